@@ -1,0 +1,164 @@
+/*
+ * qb200.h — C-ABI of the B200 (sm_100a) quantized-operator engine.
+ *
+ * This is the drop-in boundary for the hot path of JingInAI/Quantize's `quant_engine` torch extension:
+ *   tpack / tunpack                  reference: engine/kernels/tpack/tpack.h:17-32, tpack.cu:96-128, :327-359
+ *   quantconv2d_float_input          reference: engine/kernels/functions/funcs.h:143-151,
+ *                                               quantconv2d_float_input.cu:45-121 (kernel), :140-220 (host)
+ * plus the activation-quantize formula the fused conv folds in
+ *   Quantizer.simulate               reference: modelzoo/modules/quantizer.py:196-226 (q = clamp(round(x/s - z)))
+ *
+ * Everything here is plain C: device pointers, sizes, a cudaStream_t passed as void*.  No torch types.
+ * The Python-facing `quant_engine` module (quantize_b200/csrc/pybind.cpp) is a thin shim over these
+ * entry points; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative QB200_E* code on argument errors, or a positive
+ *     cudaError_t; qb200_last_error() returns a thread-local message for the last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host.
+ *   - all launches are asynchronous on `stream` (a cudaStream_t; NULL = legacy default stream).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with a CUDA error.
+ */
+#ifndef QB200_H_
+#define QB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QB200_VERSION 101
+
+/* error codes (negative; positive values are cudaError_t) */
+#define QB200_OK 0
+#define QB200_EINVAL (-1)       /* bad argument */
+#define QB200_EUNSUPPORTED (-2) /* valid in the reference but not implemented by this engine */
+#define QB200_EDRIVER (-3)      /* CUDA driver entry point (cuTensorMapEncode*) unavailable / failed */
+
+/* element types accepted by qb200_tpack (the reference dispatches AT_DISPATCH_ALL_TYPES_AND(Half), tpack.cu:120) */
+typedef enum {
+    QB200_U8 = 0,
+    QB200_I8 = 1,
+    QB200_I16 = 2,
+    QB200_I32 = 3,
+    QB200_I64 = 4,
+    QB200_F16 = 5,
+    QB200_F32 = 6,
+    QB200_F64 = 7,
+    QB200_BF16 = 8
+} qb200_dtype;
+
+int qb200_version(void);
+const char* qb200_last_error(void);
+/* number of this library's kernel launches issued by the calling thread since the last reset (bench.py's gpu_launches) */
+uint64_t qb200_launch_count(void);
+void qb200_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sub-byte packing  (reference: tpack.cu:30-84 kernel, :96-128 launcher, :203-255 host logic)
+ *
+ *   stored_i = (uint8)((int8)x_i + (sign ? 2^(n_bits-1) : 0));  stream bits [i*n, (i+1)*n) = stored_i, LSB first.
+ *   out must hold qb200_packed_bytes(n_elements, n_bits) bytes; every byte is written (pad bits = 0), so
+ *   the caller does not have to zero it (the reference needs torch::zeros, tpack.cu:225).
+ *   range_flag (device int32, may be NULL): bit 0 is OR-ed in when any element is outside
+ *   [-(2^(n-1)), 2^(n-1)-1] (signed) / [0, 2^n-1] (unsigned) or is NaN — the fused form of the reference's
+ *   x.min()/x.max() host check (tpack.cu:211-215).  The caller zeroes it before the call.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t qb200_packed_bytes(int64_t n_elements, int n_bits);
+int qb200_tpack(const void* x, int x_dtype, int64_t n_elements, int n_bits, int sign,
+                uint8_t* out, int32_t* range_flag, void* stream);
+
+/* reference: tpack.cu:267-315 kernel, :327-359 launcher.  out is int8 (sign) or uint8, n_elements long. */
+int qb200_tunpack(const uint8_t* packed, int64_t n_elements, int n_bits, int sign,
+                  void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Quantized convolution with float input  (reference: quantconv2d_float_input.cu:45-121, :140-220)
+ *
+ * Shape block shared by every conv entry point.  groups = C / Cg must divide C and K; the reference op
+ * only expresses groups == 1 (its signature has no groups argument, funcs.h:143-151) — groups > 1 is the
+ * compatible extension used for depthwise layers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t N, C, H, W;     /* input  [N, C, H, W] fp32 NCHW contiguous                         */
+    int32_t K, Cg, R, S;    /* weight [K, Cg, R, S] (weight_des[2:6]); groups = C / Cg          */
+    int32_t stride, pad;    /* square, symmetric (quantconv2dop.py:82-85)                       */
+    int32_t w_bits, w_sign; /* weight_des[0], weight_des[1]                                    */
+} qb200_conv_shape;
+
+/* P = (H + 2*pad - R)/stride + 1 (integer division, quantconv2d_float_input.cu:178-179) */
+int qb200_conv_out_hw(const qb200_conv_shape* s, int32_t* P, int32_t* Q);
+
+/* Channel padding of the quantized NHWC activation buffer and of the prepared weights:
+ * Cp = round_up(C, 32) (TMA needs 16-B pixel strides; the MMA consumes K in 32-byte slices). */
+int32_t qb200_padded_channels(int32_t C);
+
+/* Prepared (MMA-ready) weights.  A derived, cacheable view of the reference's packed byte stream — the
+ * checkpointed tensor itself is never re-laid-out.  Layout of `prepared` (all sections 256-B aligned):
+ *   wq   [K][R][S][Cgp]   one byte per weight, channel-last, zero padded.  int8 when w_sign, else uint8
+ *                         (unsigned weights feed the MMA as an unsigned B operand).
+ *                         Cgp = qb200_padded_channels(Cg) when groups == 1, else round_up(Cg, 4).
+ *   wpre int32 [K][R+1][S+1]  exclusive 2-D prefix sums over (r,s) of sum_c wq — the zero-point term of
+ *                         border pixels is a 4-corner lookup (see qb200_quantconv2d_fused).
+ */
+size_t qb200_conv_prepared_bytes(const qb200_conv_shape* s);
+int qb200_conv_prepare_weights(const qb200_conv_shape* s, const uint8_t* w_packed, void* prepared, void* stream);
+
+/* Activation quantization parameters (Quantizer.scale/zero/qmin/qmax, quantizer.py:119-123), per-tensor.
+ * DEVICE pointers to one float each, so the hot path never synchronises to read them. */
+typedef struct {
+    const float* scale;
+    const float* zero;
+    const float* qmin;
+    const float* qmax;
+} qb200_act_quant;
+
+/* workspace (bytes) the fused conv needs for the quantized NHWC activations: N*H*W*Cp */
+size_t qb200_conv_workspace_bytes(const qb200_conv_shape* s);
+
+/* q = clamp(rint(x / scale - zero), qmin, qmax) as uint8, NCHW fp32 -> NHWC(Cp) u8, channels C..Cp-1 = 0
+ * (quantizer.py:31, :215).  Exposed on its own for tests and for callers that keep activations quantized. */
+int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int32_t W,
+                            const qb200_act_quant* aq, uint8_t* q_nhwc, void* stream);
+
+/* output selector */
+#define QB200_OUT_F32 0 /* dequantized fp32 NCHW  (the op's contract)                               */
+#define QB200_OUT_ACC 1 /* raw int32 accumulators sum(qa*qw), NCHW (parity: bit-exact vs the oracle) */
+
+/* conv kernel selector (tests and benchmarks; 0 is what the product uses) */
+#define QB200_ALGO_AUTO 0   /* tcgen05 implicit GEMM when groups == 1, CUDA-core kernel otherwise       */
+#define QB200_ALGO_DIRECT 1 /* CUDA-core direct conv (any groups)                                      */
+#define QB200_ALGO_UMMA 2   /* TMA im2col + tcgen05.mma kind::i8 + TMEM accumulators (groups == 1)      */
+void qb200_set_conv_algo(int algo);
+int qb200_get_conv_algo(void);
+
+/* The fused hot path: activation-quantize + int8 implicit-GEMM conv + per-channel dequant + bias.
+ *   out[n,k,p,q] = s_a * w_scale[k|0] * ( sum qa*qw + z_a * sum_{in-bounds taps} qw ) + bias[k]
+ * which equals the reference module's packed forward (quantconv2d.py:207-210) for symmetric weights
+ * (w_zero == 0, the only case the shipped configs produce, range/minmax.py:123-135).
+ * w_scale: n_w_scale == 1 (per-tensor) or K (per-channel), as in quantconv2d_float_input.cu:104-106.
+ * w_zero must be all-zero for this entry point (checked by the caller; see qb200_quantconv2d_weightonly).
+ * bias may be NULL.  out: fp32 or int32 [N,K,P,Q] NCHW. */
+int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const void* prepared,
+                            const float* w_scale, int32_t n_w_scale, const float* bias,
+                            const qb200_act_quant* aq, void* workspace, void* out, int32_t out_kind,
+                            void* stream);
+
+/* Same conv on already-quantized NHWC(Cp) activations (the second half of the fused op). */
+int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared,
+                         const float* w_scale, int32_t n_w_scale, const float* bias,
+                         const qb200_act_quant* aq, void* out, int32_t out_kind, void* stream);
+
+/* Weight-only semantic of the reference op (8-argument call, no activation quantizer):
+ *   out = bias + sum x * ((qw - w_zero[k|0]) * w_scale[k|0])        quantconv2d_float_input.cu:83-119
+ * fp32 accumulate.  groups must be 1 (as in the reference). */
+int qb200_quantconv2d_weightonly(const qb200_conv_shape* s, const float* x, const uint8_t* w_packed,
+                                 const float* w_scale, const float* w_zero, int32_t n_w_scale,
+                                 const float* bias, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QB200_H_ */

@@ -1,0 +1,21 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): binding shim for the UNMODIFIED reference sources.
+//
+// Builds the reference implementation of the hot path straight from the files where they lie
+// under /root/reference/engine/kernels (never copied into this repo) so that tests/ and
+// bench.py's `--impl reference` / cpu_baseline leg can call the reference's own code:
+//   tpack / tunpack            -> /root/reference/engine/kernels/tpack/tpack.cu:203-255, :429-476
+//   quantconv2d_float_input    -> /root/reference/engine/kernels/functions/quantconv2d_float_input.cu:140-220
+// The reference's own pybind.cpp (engine/kernels/pybind.cpp:7-17) registers all 8 ops and would pull
+// in the five off-path .cu files; this shim registers only the three on-path ops under a different
+// module name so it can be imported next to the product's `quant_engine`.
+#include <pybind11/pybind11.h>
+#include <torch/extension.h>
+#include "tpack/tpack.h"
+#include "functions/funcs.h"
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m)
+{
+    m.def("tpack", &tpack, "reference tpack");
+    m.def("tunpack", &tunpack, "reference tunpack");
+    m.def("quantconv2d_float_input", &quantconv2d_float_input, "reference quantconv2d_float_input");
+}

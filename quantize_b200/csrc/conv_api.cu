@@ -1,0 +1,64 @@
+// C-ABI entry points of the fused quantized convolution (see include/qb200.h).
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace qb200 {
+namespace {
+
+int g_conv_algo = QB200_ALGO_AUTO;
+
+int run_conv_q8(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared, const float* w_scale,
+                int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind,
+                cudaStream_t st) {
+    QB_REQUIRE(n_w_scale == 1 || n_w_scale == s->K, QB200_EINVAL, "weight_scale must have 1 or K elements");
+    QB_REQUIRE(out_kind == QB200_OUT_F32 || out_kind == QB200_OUT_ACC, QB200_EINVAL, "conv: bad out_kind");
+    QB_REQUIRE(aq && aq->scale && aq->zero, QB200_EINVAL, "conv: activation quantizer parameters missing");
+    QB_REQUIRE(q_nhwc && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
+    const ConvGeom g = make_geom(*s);
+    const PreparedLayout L = prepared_layout(*s);
+    const uint8_t* wq = static_cast<const uint8_t*>(prepared);
+    EpilogueParams ep;
+    ep.a_scale = aq->scale;
+    ep.a_zero = aq->zero;
+    ep.w_scale = w_scale;
+    ep.bias = bias;
+    ep.wpre = reinterpret_cast<const int32_t*>(wq + L.wpre_off);
+    ep.per_tensor_w = n_w_scale == 1;
+    ep.out_kind = out_kind;
+
+    int algo = g_conv_algo;
+    if (algo == QB200_ALGO_AUTO) algo = umma_supported(g) ? QB200_ALGO_UMMA : QB200_ALGO_DIRECT;
+    if (algo == QB200_ALGO_UMMA) return launch_conv_umma(g, q_nhwc, wq, ep, out, st);
+    return launch_conv_direct(g, q_nhwc, wq, ep, out, st);
+}
+
+}  // namespace
+}  // namespace qb200
+
+extern "C" {
+
+void qb200_set_conv_algo(int algo) { qb200::g_conv_algo = algo; }
+int qb200_get_conv_algo(void) { return qb200::g_conv_algo; }
+
+int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared, const float* w_scale,
+                         int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind,
+                         void* stream) {
+    using namespace qb200;
+    if (int rc = validate_shape(s)) return rc;
+    if (s->N == 0) return 0;
+    return run_conv_q8(s, q_nhwc, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, static_cast<cudaStream_t>(stream));
+}
+
+int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
+                            int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* workspace, void* out,
+                            int32_t out_kind, void* stream) {
+    using namespace qb200;
+    if (int rc = validate_shape(s)) return rc;
+    if (s->N == 0) return 0;
+    QB_REQUIRE(workspace != nullptr, QB200_EINVAL, "conv: workspace missing (qb200_conv_workspace_bytes)");
+    if (int rc = qb200_act_quantize_nhwc(x, s->N, s->C, s->H, s->W, aq, static_cast<uint8_t*>(workspace), stream)) return rc;
+    return run_conv_q8(s, static_cast<const uint8_t*>(workspace), prepared, w_scale, n_w_scale, bias, aq, out, out_kind,
+                       static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

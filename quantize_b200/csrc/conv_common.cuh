@@ -1,0 +1,94 @@
+// Geometry + dequant epilogue shared by the CUDA-core and the tcgen05 convolution kernels.
+#pragma once
+#include "common.cuh"
+
+namespace qb200 {
+
+struct ConvGeom {
+    int N, C, H, W, K, Cg, R, S, stride, pad, P, Q;
+    int groups, Cp, Cgp, w_sign;
+};
+
+struct PreparedLayout {
+    int Cgp;
+    size_t wq_bytes;
+    size_t wpre_off;
+    size_t total;
+};
+PreparedLayout prepared_layout(const qb200_conv_shape& s);
+int validate_shape(const qb200_conv_shape* s);
+
+static inline ConvGeom make_geom(const qb200_conv_shape& s) {
+    ConvGeom g;
+    g.N = s.N; g.C = s.C; g.H = s.H; g.W = s.W; g.K = s.K; g.Cg = s.Cg; g.R = s.R; g.S = s.S;
+    g.stride = s.stride; g.pad = s.pad;
+    g.P = (s.H + 2 * s.pad - s.R) / s.stride + 1;  // quantconv2d_float_input.cu:178
+    g.Q = (s.W + 2 * s.pad - s.S) / s.stride + 1;  // :179
+    g.groups = s.C / s.Cg;
+    g.Cp = qb200_padded_channels(s.C);
+    g.Cgp = prepared_layout(s).Cgp;
+    g.w_sign = s.w_sign ? 1 : 0;
+    return g;
+}
+
+// out = s_a * s_w[k] * (acc + z_a * wsum_valid(k, p, q)) + bias[k]
+struct EpilogueParams {
+    const float* a_scale;   // device, 1 element
+    const float* a_zero;    // device, 1 element
+    const float* w_scale;   // device, 1 or K elements
+    const float* bias;      // device, K elements or null
+    const int32_t* wpre;    // device, [K][R+1][S+1]
+    int per_tensor_w;
+    int out_kind;
+};
+
+struct EpilogueScalars {
+    float s_a, z_a;
+};
+
+// in-bounds tap window of an output pixel: taps r in [r0, r1), s in [s0, s1)
+struct PixelWindow {
+    int r0, r1, s0, s1;
+};
+
+__device__ __forceinline__ EpilogueScalars load_epilogue_scalars(const EpilogueParams& ep) {
+    EpilogueScalars es;
+    es.s_a = __ldg(ep.a_scale);
+    es.z_a = __ldg(ep.a_zero);
+    return es;
+}
+
+__device__ __forceinline__ PixelWindow pixel_window(const ConvGeom& g, int p, int q) {
+    PixelWindow w;
+    const int h0 = p * g.stride - g.pad, w0 = q * g.stride - g.pad;  // quantconv2d_float_input.cu:89-90
+    w.r0 = max(0, -h0);
+    w.r1 = min(g.R, g.H - h0);
+    w.s0 = max(0, -w0);
+    w.s1 = min(g.S, g.W - w0);
+    return w;
+}
+
+__device__ __forceinline__ int32_t window_wsum(const int32_t* __restrict__ wpre, int k, int R, int S,
+                                               const PixelWindow& w) {
+    const int32_t* t = wpre + (int64_t)k * (R + 1) * (S + 1);
+    const int s1 = S + 1;
+    return __ldg(t + w.r1 * s1 + w.s1) - __ldg(t + w.r0 * s1 + w.s1) - __ldg(t + w.r1 * s1 + w.s0) +
+           __ldg(t + w.r0 * s1 + w.s0);
+}
+
+__device__ __forceinline__ float dequant_one(int32_t acc, int k, const ConvGeom& g, const EpilogueParams& ep,
+                                             const EpilogueScalars& es, const PixelWindow& pw) {
+    float t = (float)acc;
+    if (es.z_a != 0.f) t = __fmaf_rn(es.z_a, (float)window_wsum(ep.wpre, k, g.R, g.S, pw), t);
+    const float sw = __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k));
+    const float b = ep.bias ? __ldg(ep.bias + k) : 0.f;
+    return __fmaf_rn(__fmul_rn(es.s_a, sw), t, b);
+}
+
+int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
+                       cudaStream_t st);
+int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
+                     cudaStream_t st);
+bool umma_supported(const ConvGeom& g);
+
+}  // namespace qb200

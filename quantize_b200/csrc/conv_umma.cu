@@ -1,0 +1,453 @@
+// Kernel A: int8 implicit-GEMM convolution on the 5th-generation tensor cores (sm_100a only).
+//
+// Replaces the per-output-element scalar loop of the reference (quantconv2d_float_input.cu:45-121) for
+// groups == 1.  GEMM view:  D[M = N*P*Q pixels][N = K out-channels] = A[M][Kg = R*S*Cp] * B[Kg][N]
+//   A  = im2col of the quantized NHWC(Cp) u8 activations — never materialised: the TMA unit gathers each
+//        128-pixel x KC-channel slice of one filter tap straight into swizzled shared memory
+//        (cp.async.bulk.tensor.4d ... im2col; out-of-image taps are zero-filled by the hardware, which is
+//        exactly the reference's bounds check at :92);
+//   B  = prepared weights [K][R][S][Cp] (K-major), fetched with a tiled 2-D TMA;
+//   D  = int32 accumulators in TMEM (tcgen05.mma.cta_group::1.kind::i8, u8 x s8 -> s32), double buffered so the
+//        epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> dequant -> coalesced NCHW stores: a TMEM lane is an output pixel, so the 32
+// lanes of a warp write 32 consecutive pixels of one output channel = one 128-byte line).
+// Persistent: grid = #SMs, static round-robin tile schedule, output-channel tiles fastest so concurrently
+// running CTAs share the same activation slice in L2.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+#include <cuda.h>
+
+namespace qb200 {
+namespace {
+
+constexpr int kBM = 128;            // pixels per tile = TMEM lanes = UMMA M
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
+constexpr int kMaxStages = 8;
+constexpr size_t kSmemBudget = 200 * 1024;
+
+struct UmmaParams {
+    ConvGeom g;
+    EpilogueParams ep;
+    int KC;            // channel bytes per k-block: 32, 64 or 128 (== swizzle span)
+    int BN;            // out-channel tile: 64, 128 or 256
+    int stages;
+    int cblocks;       // Cp / KC
+    int m_tiles, n_tiles;
+    int64_t M;         // N*P*Q
+    uint32_t idesc;
+    uint32_t sbo16;    // stride-byte-offset >> 4 (8 rows * KC bytes)
+    uint32_t layout;   // UMMA smem layout type
+    int* err_flag;     // device int: set non-zero by the watchdog
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a lost arrival must not hang the GPU — after ~4 s the kernel flags the error and traps.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000ll) {
+            if (err_flag) atomicExch(err_flag, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c, int w, int h,
+                                                   int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"(off_w), "h"(off_h)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], u8 x s8 -> s32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (tcgen05): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo16, uint32_t layout) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset: unused for swizzled K-major, canonical value 1
+    d |= (uint64_t)(sbo16 & 0x3FFF) << 32;  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const UmmaParams prm, void* __restrict__ out) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+
+    const ConvGeom& g = prm.g;
+    const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
+    const uint32_t a_bytes = kBM * KC, b_bytes = BN * KC, stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint64_t* full = bars;                     // [stages]
+    uint64_t* empty = bars + kMaxStages;       // [stages]
+    uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
+    uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int total_tiles = prm.m_tiles * prm.n_tiles;
+    const int kblocks = g.R * g.S * prm.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int PQ = g.P * g.Q;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % prm.n_tiles;
+                const int m_tile = tile / prm.n_tiles;
+                const int64_t m0 = (int64_t)m_tile * kBM;
+                const int img = (int)(m0 / PQ);
+                const int rem = (int)(m0 - (int64_t)img * PQ);
+                const int p0 = rem / g.Q, q0 = rem - p0 * g.Q;
+                const int cw = q0 * g.stride - g.pad, ch = p0 * g.stride - g.pad;
+                for (int r = 0; r < g.R; ++r)
+                    for (int s = 0; s < g.S; ++s)
+                        for (int cb = 0; cb < prm.cblocks; ++cb) {
+                            mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 1);
+                            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                            uint8_t* sb = sa + a_bytes;
+                            mbar_expect_tx(&full[stage], stage_bytes);
+                            tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
+                            tma_load_2d(sb, &tmap_b, &full[stage], (r * g.S + s) * g.Cp + cb * KC, n_tile * BN);
+                            if (++stage == stages) { stage = 0; phase ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int buf = 0;
+            uint32_t acc_phase = 0;
+            const int n_mma = KC / 32;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[stage], phase, prm.err_flag, 3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
+                    const uint64_t adesc = make_smem_desc(sa, prm.sbo16, prm.layout);
+                    const uint64_t bdesc = make_smem_desc(sb, prm.sbo16, prm.layout);
+                    for (int k = 0; k < n_mma; ++k)  // advance 32 bytes of K inside the swizzle atom: +2 in >>4 units
+                        umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), prm.idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&acc_full[buf]);  // accumulator complete
+                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;
+        const int PQ = g.P * g.Q;
+        const EpilogueScalars es = load_epilogue_scalars(prm.ep);
+        int buf = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % prm.n_tiles;
+            const int m_tile = tile / prm.n_tiles;
+            const int64_t m = (int64_t)m_tile * kBM + row;
+            const bool row_ok = m < prm.M;
+            const int img = row_ok ? (int)(m / PQ) : 0;
+            const int pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
+            const int p = pq / g.Q, q = pq - p * g.Q;
+            const PixelWindow pw = pixel_window(g, p, q);
+            const int k_base = n_tile * BN;
+            const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
+
+            mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride);
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(taddr + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (row_ok) {
+                    if (prm.ep.out_kind == QB200_OUT_ACC) {
+                        int32_t* o = static_cast<int32_t*>(out) + o_base + (int64_t)c0 * PQ;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (k_base + c0 + j < g.K) o[(int64_t)j * PQ] = (int32_t)v[j];
+                    } else {
+                        float* o = static_cast<float*>(out) + o_base + (int64_t)c0 * PQ;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int k = k_base + c0 + j;
+                            if (k < g.K) o[(int64_t)j * PQ] = dequant_one((int32_t)v[j], k, g, prm.ep, es, pw);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps through the driver entry points (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DriverApi {
+    EncodeTiledFn tiled = nullptr;
+    EncodeIm2colFn im2col = nullptr;
+    int driver_version = 0;
+    bool ok = false;
+};
+
+const DriverApi& driver_api() {
+    static DriverApi api = [] {
+        DriverApi a;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            a.tiled = reinterpret_cast<EncodeTiledFn>(f);
+        f = nullptr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            a.im2col = reinterpret_cast<EncodeIm2colFn>(f);
+        cudaDriverGetVersion(&a.driver_version);
+        a.ok = a.tiled && a.im2col;
+        return a;
+    }();
+    return api;
+}
+
+int* watchdog_flag() {
+    // one device int per (thread, device); leaked on purpose (process lifetime)
+    static thread_local int* flags[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!flags[dev]) {
+        int* p = nullptr;
+        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
+        cudaMemset(p, 0, sizeof(int));
+        flags[dev] = p;
+    }
+    return flags[dev];
+}
+
+int num_sms() {
+    static thread_local int cached[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return kNumSMs;
+    if (!cached[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+}  // namespace
+
+bool umma_supported(const ConvGeom& g) {
+    if (g.groups != 1) return false;
+    if (g.pad > 128 || g.pad - (g.R - 1) < -128 || g.pad - (g.S - 1) < -128) return false;  // im2col corner range
+    if (g.stride > 8) return false;  // TMA element strides
+    if ((int64_t)g.W * g.Cp >= (1ll << 32) || (int64_t)g.H * g.W * g.Cp >= (1ll << 40)) return false;
+    return true;
+}
+
+int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
+                     cudaStream_t st) {
+    QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
+    const DriverApi& api = driver_api();
+    QB_REQUIRE(api.ok, QB200_EDRIVER, "cuTensorMapEncodeTiled/Im2col driver entry points unavailable");
+    QB_REQUIRE(reinterpret_cast<uintptr_t>(qa) % 16 == 0 && reinterpret_cast<uintptr_t>(wq) % 16 == 0, QB200_EINVAL,
+               "conv_umma: operands must be 16-B aligned");
+
+    UmmaParams prm;
+    prm.g = g;
+    prm.ep = ep;
+    prm.M = (int64_t)g.N * g.P * g.Q;
+    if (prm.M == 0) return 0;
+    prm.KC = (g.Cp % 128 == 0) ? 128 : (g.Cp % 64 == 0) ? 64 : 32;
+    prm.cblocks = g.Cp / prm.KC;
+    prm.m_tiles = (int)ceil_div64(prm.M, kBM);
+    const int sms = num_sms();
+    // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
+    int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
+    while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
+    prm.BN = BN;
+    prm.n_tiles = (g.K + BN - 1) / BN;
+    const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
+    int stages = (int)((kSmemBudget - 2048) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
+    prm.stages = stages;
+    prm.layout = prm.KC == 128 ? 2u : (prm.KC == 64 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
+    prm.sbo16 = (uint32_t)(8 * prm.KC) >> 4;
+    // instruction descriptor: D=s32, A=u8, B=s8|u8, both K-major, N>>3, M>>4
+    prm.idesc = (2u << 4) | (0u << 7) | ((g.w_sign ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    prm.err_flag = watchdog_flag();
+
+    const CUtensorMapSwizzle swz = prm.KC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : prm.KC == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
+    alignas(64) CUtensorMap tmap_a, tmap_b;
+    {
+        // activations: (C, W, H, N) u8, im2col mode; base pixel of an output (p,q) is (q*stride - pad, p*stride - pad)
+        cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.Cp, (cuuint64_t)g.W * g.Cp, (cuuint64_t)g.H * g.W * g.Cp};
+        int lower[2] = {-g.pad, -g.pad};
+        int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
+        cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+        CUresult r = api.im2col(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(qa), dims, strides, lower,
+                                upper, (cuuint32_t)prm.KC, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+        // driver <= 13.1 encodes im2col maps of tensors below 128 KiB with a bit that makes the unit fault;
+        // the same adjustment NVIDIA's own CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp)
+        if (api.driver_version <= 13010 && (size_t)g.N * g.H * g.W * g.Cp < 131072)
+            reinterpret_cast<uint64_t*>(&tmap_a)[1] &= ~(1ull << 21);
+    }
+    {
+        // weights: [K rows][R*S*Cp bytes], tiled mode, rows beyond K zero-filled
+        cuuint64_t dims[2] = {(cuuint64_t)g.R * g.S * g.Cp, (cuuint64_t)g.K};
+        cuuint64_t strides[1] = {(cuuint64_t)g.R * g.S * g.Cp};
+        cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)BN};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = api.tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(wq), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    }
+
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    static thread_local size_t smem_set = 0;
+    if (smem > smem_set) {
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048)));
+        smem_set = kSmemBudget + 2048;
+    }
+    const int total_tiles = prm.m_tiles * prm.n_tiles;
+    const int grid = total_tiles < sms ? total_tiles : sms;
+    conv_umma_kernel<<<grid, kThreads, smem, st>>>(tmap_a, tmap_b, prm, out);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace qb200
