@@ -1,0 +1,372 @@
+"""bench.py — BASELINE.json's metric: ResNet-50 W8A8 images/s (conv stack through the fused hot path).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            one JSON line (this engine)
+  python bench.py --impl reference [...]                          one JSON line (the reference's CPU path, host cores)
+  torchrun --nproc-per-node N bench.py --gpus N ...               one process per GPU, weak scaling (256 images / GPU)
+
+A step = one pass of the hot path over one batch: the 53 convolutions of ResNet-50 at batch 256, every layer through
+qb200_act_quantize_nhwc + qb200_conv2d_q8_nhwc (the two kernels of quant_engine.quantconv2d_float_input's fused
+path) on its own synthetic fp32 NCHW input that is resident in HBM when the timed region starts.
+  value      images/s over all ranks, device-timed (CUDA events, max over ranks)
+  e2e        the same metric through the public API a user calls — the packed ResNet-50 built from host.QuantConv2d
+             layers, whose convs call quant_engine.quantconv2d_float_input — from PINNED HOST images to HOST logits,
+             host<->device copies inside the timed region
+  roofline   the dominant kernel (conv_umma_kernel): algorithmic bytes per launch / measured duration vs measured HBM peak
+  cpu_baseline  the reference's CPU fake-quant conv path (oracle/fakequant.py port) on a bounded sample, rank 0, N=1
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODEL = "resnet50"
+PER_GPU_BATCH = 256
+W_BITS, A_BITS = 8, 8
+INT8_PEAK_TOPS = 4500.0  # B200 dense int8 spec
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU (BASELINE: 256)")
+    ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", default="", help="debug: comma-separated layer indices to run")
+    ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured", d
+    return 6650.0, "fallback", {}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi) during the timed region
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [p.strip() for p in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference arm / cpu baseline: reference's CPU fake-quant conv path (port), all host threads
+# ---------------------------------------------------------------------------------------------------
+def cpu_fakequant_stack(model, sample_batch, steps, warmup):
+    import torch
+    from quantize_b200 import models
+    from oracle.fakequant import FakeQuantConvStack          # the one place bench.py executes oracle/
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    specs = models.conv_layer_specs(model, sample_batch)
+    stack = FakeQuantConvStack(specs, sample_batch, W_BITS, A_BITS)
+    sec = stack.time_steps(steps, warmup)
+    return sample_batch / sec, sec, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8
+    ips, sec, cores = cpu_fakequant_stack(args.model, sample, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "ResNet-50 W8A8 images/sec", "value": round(ips, 3), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model} conv stack (53 convs) W{W_BITS}A{A_BITS} fake-quant on host CPU, "
+                               f"bounded sample of {sample} images per step"},
+        "cpu_baseline": {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images/step x {args.steps} steps: Quantizer.simulate (act+weight) + fp32 "
+                                   f"F.conv2d per layer (reference quantconv2d.py:154-168), torch {cores} threads"},
+        "e2e": {"value": round(ips, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# this engine
+# ---------------------------------------------------------------------------------------------------
+class ConvStack:
+    """per-layer device operands for the C-ABI hot path"""
+
+    def __init__(self, specs, device, seed=0):
+        import torch
+        from quantize_b200 import capi, engine
+        self.torch, self.capi = torch, capi
+        self.L = capi.lib()
+        qe = engine.load()
+        g = torch.Generator(device=device).manual_seed(seed)
+        self.layers = []
+        max_ws = max_out = 0
+        for i, s in enumerate(specs):
+            x = torch.randn(s["N"], s["C"], s["H"], s["W"], generator=g, device=device)
+            if s["relu_input"]:
+                x.relu_()
+            cg = s["C"] // s["groups"]
+            qw = torch.randint(-127, 128, (s["K"], cg, s["R"], s["R"]), generator=g, device=device).float()
+            packed, des = qe.tpack(qw, W_BITS, True)             # reference format (tpack.cu:203-255)
+            shape = capi.conv_shape(s["N"], s["C"], s["H"], s["W"], s["K"], cg, s["R"], s["R"], s["stride"], s["pad"],
+                                    W_BITS, 1)
+            prepared = torch.empty(self.L.qb200_conv_prepared_bytes(ctypes.byref(shape)), dtype=torch.uint8, device=device)
+            capi.check(self.L.qb200_conv_prepare_weights(ctypes.byref(shape), packed.data_ptr(), prepared.data_ptr(), None),
+                       "prepare")
+            qmax = float((1 << A_BITS) - 1)
+            xmin, xmax = x.min(), x.max()
+            a_scale = ((xmax - xmin) / qmax).reshape(1)
+            a_zero = (xmin / a_scale).reshape(1)                  # range/minmax.py:136-143
+            aq_t = [a_scale, a_zero, torch.zeros(1, device=device), torch.full((1,), qmax, device=device)]
+            aq = capi.ActQuant(*[t.data_ptr() for t in aq_t])
+            w_scale = torch.rand(s["K"], generator=g, device=device) * 1e-3 + 1e-4
+            bias = torch.randn(s["K"], generator=g, device=device)
+            P, Q = capi.conv_out_hw(shape)
+            Cp = self.L.qb200_padded_channels(s["C"])
+            max_ws = max(max_ws, self.L.qb200_conv_workspace_bytes(ctypes.byref(shape)))
+            max_out = max(max_out, s["N"] * s["K"] * P * Q)
+            ops = 2 * s["N"] * s["K"] * P * Q * cg * s["R"] * s["R"]
+            conv_bytes = s["N"] * s["H"] * s["W"] * Cp + s["K"] * s["R"] * s["R"] * Cp + 4 * s["N"] * s["K"] * P * Q + 12 * s["K"]
+            quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * s["H"] * s["W"] * Cp
+            self.layers.append(dict(spec=s, x=x, shape=shape, prepared=prepared, aq=aq, aq_t=aq_t, w_scale=w_scale,
+                                    bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed))
+        self.ws = torch.empty(max_ws, dtype=torch.uint8, device=device)
+        self.out = torch.empty(max_out, dtype=torch.float32, device=device)
+        torch.cuda.synchronize()
+
+    def step(self, stream, events=None):
+        """one pass of the hot path; events: optional list of (start, end) CUDA events around each conv launch"""
+        L, capi = self.L, self.capi
+        for i, l in enumerate(self.layers):
+            s = l["spec"]
+            capi.check(L.qb200_act_quantize_nhwc(l["x"].data_ptr(), s["N"], s["C"], s["H"], s["W"], ctypes.byref(l["aq"]),
+                                                 self.ws.data_ptr(), stream), "act_quantize")
+            if events is not None:
+                events[i][0].record()
+            capi.check(L.qb200_conv2d_q8_nhwc(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
+                                              l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(), ctypes.byref(l["aq"]),
+                                              self.out.data_ptr(), capi.OUT_F32, stream), "conv")
+            if events is not None:
+                events[i][1].record()
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from quantize_b200 import capi, models
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0 and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    n_gpus = world
+
+    specs = models.conv_layer_specs(args.model, args.batch)
+    if args.layers:
+        keep = [int(v) for v in args.layers.split(",")]
+        specs = [specs[i] for i in keep]
+    stack = ConvStack(specs, device, seed=rank)
+    L = capi.lib()
+    stream_obj = torch.cuda.current_stream()
+    stream = ctypes.c_void_p(stream_obj.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident hot path -------------------------------------------------------------------
+    for _ in range(max(args.warmup, 1)):
+        stack.step(stream)
+    K = args.steps
+    nl = len(stack.layers)
+    events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
+              for _ in range(K)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    L.qb200_launch_count_reset()
+    t0.record()
+    for k in range(K):
+        stack.step(stream, events[k])
+    t1.record()
+    barrier()
+    launches = int(L.qb200_launch_count())
+    clocks = sampler.stop()
+    ms = t0.elapsed_time(t1)
+    conv_ms = [sum(events[k][i][0].elapsed_time(events[k][i][1]) for k in range(K)) / K for i in range(nl)]
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lc = torch.tensor([launches], device=device, dtype=torch.int64)
+        dist.all_reduce(lc)
+        launches = int(lc.item())
+    ms_per_step = ms / K
+    value = args.batch * n_gpus / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (conv_umma_kernel), rank 0 ------------------------------------
+    hbm_peak, peak_kind, peaks = measured_peaks()
+    conv_total_ms = sum(conv_ms)
+    conv_bytes = sum(l["conv_bytes"] for l in stack.layers)
+    total_ops = sum(l["ops"] for l in stack.layers)
+    contract_bytes = models.conv_stack_work(specs, W_BITS)[1]
+    achieved = conv_bytes / nl / (conv_total_ms / nl * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "conv_umma_traffic.json")
+    if os.path.exists(tp) and not args.layers and args.batch == PER_GPU_BATCH:
+        with open(tp) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "conv_umma_kernel", "achieved": round(achieved, 1), "peak": hbm_peak,
+                "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_kind,
+                "bytes_per_launch": round(conv_bytes / nl), "us_per_launch": round(conv_total_ms / nl * 1e3, 2),
+                "launches_per_step": nl,
+                "conv_share_of_step": round(conv_total_ms / ms_per_step, 4),
+                "tensor_tops": round(total_ops / (conv_total_ms * 1e-3) / 1e12, 1),
+                "tensor_frac_of_int8_spec": round(total_ops / (conv_total_ms * 1e-3) / 1e12 / INT8_PEAK_TOPS, 4),
+                "step_contract_gbs": round(contract_bytes / (ms_per_step * 1e-3) / 1e9, 1),
+                "step_contract_frac": round(contract_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak, 4)}
+    if args.per_layer and rank == 0:
+        for i, l in enumerate(stack.layers):
+            s = l["spec"]
+            print(f"layer {i:2d} C{s['C']:4d} H{s['H']:3d} K{s['K']:4d} R{s['R']} s{s['stride']} conv {conv_ms[i]*1e3:8.1f} us "
+                  f"{l['conv_bytes']/conv_ms[i]/1e6:7.0f} GB/s {l['ops']/conv_ms[i]/1e9:7.0f} TOPS", file=sys.stderr)
+
+    # ---- end to end through the public op API: host images -> logits on host ----------------------------
+    e2e = None
+    if not args.no_e2e and not args.layers:
+        del stack
+        torch.cuda.empty_cache()
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0)
+        hw = models.INPUT_HW[args.model]
+        host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+        host_out = torch.empty(args.batch, 1000, dtype=torch.float32).pin_memory()
+        dev_in = torch.empty_like(host_in, device=device)
+
+        def e2e_step():
+            dev_in.copy_(host_in, non_blocking=True)
+            with torch.no_grad():
+                logits = net(dev_in)
+            host_out.copy_(logits, non_blocking=True)
+
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
+        barrier()
+        L.qb200_launch_count_reset()
+        wall0 = time.perf_counter()
+        t0.record()
+        for _ in range(K):
+            e2e_step()
+        t1.record()
+        barrier()
+        wall = time.perf_counter() - wall0
+        e_ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([e_ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = float(t.item())
+        e2e = {"value": round(args.batch * n_gpus / (e_ms / K / 1e3), 1), "unit": "images/s",
+               "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
+               "ms_per_step": round(e_ms / K, 3), "wall_ms_per_step": round(wall / K * 1e3, 3),
+               "api": "models.build_packed(resnet50) forward: host.QuantConv2d -> quant_engine.quantconv2d_float_input",
+               "engine_launches_per_step": int(L.qb200_launch_count()) // K}
+
+    cpu_baseline = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and not args.layers:
+        ips, sec, cores = cpu_fakequant_stack(args.model, 8, 3, 1)
+        cpu_baseline = {"value": round(ips, 3), "unit": "images/s", "cores": cores, "kind": "port",
+                        "sample": "8 images/step x 3 steps (1 warm-up): Quantizer.simulate (act+weight) + fp32 F.conv2d "
+                                  "per layer, the reference's CPU fake-quant path (quantconv2d.py:154-168)"}
+
+    if rank == 0:
+        line = {
+            "metric": "ResNet-50 W8A8 images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": n_gpus,
+            "steps": K, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 x s8 -> s32 (fp32 dequant)", "data": "synthetic",
+            "config": {"workload": f"{args.model} conv stack: {nl} convs via quantconv2d_float_input fused path "
+                                   f"(act-quantize + tcgen05 int8 implicit GEMM + dequant), fp32 NCHW in/out per layer",
+                       "per_gpu_batch": args.batch, "global_batch": args.batch * n_gpus, "w_bits": W_BITS, "a_bits": A_BITS,
+                       "parallelism": f"batch-sharded x{n_gpus}, weights replicated, no collective on the data path",
+                       "l2": "every layer streams its own input/output: 22.3 GB per step >> 126 MB L2, no flush needed",
+                       "ops_per_step": total_ops, "contract_bytes_per_step": contract_bytes},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's quantized conv layer, routed through the B200 engine.
+
+The reference's own modules (modelzoo/modules/quantconv2d.py, quantizer.py, range/minmax.py) stay unchanged and can
+use this engine directly.  They are not available on a machine without the reference checkout, so
+this file restates — same names, same argument meaning, same arithmetic — the part of their interface the hot path
+needs:  MinMax / MAMinMax range estimation, Quantizer (calibrate / simulate / pack) and QuantConv2d
+(BN folding, calibrate, fake-quant `_forward`, `pack()`, packed `forward`).  The one intended difference is the
+packed `forward`: the reference has the op call commented out and runs a float F.conv2d (quantconv2d.py:198-210);
+here it calls `quant_engine.quantconv2d_float_input` with the activation quantizer's parameters (the fused path).
+
+All tensor math in this file is calibration-time PyTorch (plumbing); the inference arithmetic is in csrc/.
+"""
+from copy import deepcopy
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import engine as _engine
+
+
+class MinMax:
+    """reference modelzoo/modules/range/minmax.py:12-145 (percentile == 0 only)."""
+
+    def __init__(self, n_bits=8, symmetric=True, signed=True, granularity="layer", percentile=0.0):
+        assert percentile == 0.0, "percentile ranges are calibration-only features outside this mirror"
+        self.n_bits, self.symmetric, self.signed, self.granularity = n_bits, symmetric, signed, granularity
+
+    def update(self, xmin, xmax):                                   # minmax.py:44-60
+        if "xmin" not in self.__dict__:
+            self.xmin, self.xmax = xmin, xmax
+        else:
+            self.xmin, self.xmax = torch.min(self.xmin, xmin), torch.max(self.xmax, xmax)
+        return self.xmin, self.xmax
+
+    def range(self, x: Tensor, flag: str):                          # minmax.py:62-108
+        if self.granularity in ("L", "Layer", "layer"):
+            x = x.flatten(0)
+            xmin = x.min() if not self.symmetric else torch.tensor(0.0).to(x.device)
+            xmax = x.max() if not self.symmetric else x.abs().max()
+        elif self.granularity in ("C", "Channel", "channel"):
+            if flag == "activation":
+                x = x.transpose(0, 1)
+            x = x.flatten(1)
+            xmin = x.min(dim=1)[0] if not self.symmetric else torch.zeros(x.shape[0]).to(x.device)
+            xmax = x.max(dim=1)[0] if not self.symmetric else x.abs().max(dim=1)[0]
+        else:
+            raise NotImplementedError(f"Granularity {self.granularity} not implemented.")
+        return self.update(xmin, xmax)
+
+    def quantize(self, xmin: Tensor, xmax: Tensor):                 # minmax.py:110-145
+        n_bits = self.n_bits
+        if self.symmetric:
+            if self.signed:
+                qmax, qmin = (1 << (n_bits - 1)) - 1, -(1 << (n_bits - 1))
+                quant_range = float(qmax - qmin - 1) / 2
+            else:
+                qmax, qmin = (1 << n_bits) - 1, 0
+                quant_range = float(qmax - qmin)
+            scale = torch.max(xmin.abs(), xmax.abs()) / quant_range
+            zero = torch.zeros_like(scale)
+        else:
+            qmax, qmin = (1 << n_bits) - 1, 0
+            scale = (xmax - xmin) / float(qmax - qmin)
+            zero = xmin / scale
+        return scale, zero, qmin, qmax
+
+    def __call__(self, flag: str, x: Tensor, **kwargs):
+        return self.quantize(*self.range(x, flag))
+
+
+class MAMinMax(MinMax):
+    """reference minmax.py:148-203: moving-average min/max."""
+
+    def __init__(self, momentum=0.1, **kw):
+        super().__init__(**kw)
+        self.momentum = momentum
+
+    def update(self, xmin, xmax):
+        if "xmin" not in self.__dict__:
+            self.xmin, self.xmax = xmin, xmax
+        elif 0.0 <= self.momentum <= 1.0:
+            self.xmin = self.momentum * xmin + (1 - self.momentum) * self.xmin
+            self.xmax = self.momentum * xmax + (1 - self.momentum) * self.xmax
+        else:
+            self.xmin, self.xmax = torch.min(self.xmin, xmin), torch.max(self.xmax, xmax)
+        return self.xmin, self.xmax
+
+
+RANGES = {"minmax": MinMax, "maminmax": MAMinMax}
+
+
+class Quantizer(nn.Module):
+    """reference modelzoo/modules/quantizer.py:43-306 (no adaround / awq / static_scale)."""
+
+    def __init__(self, n_bits=8, symmetric=True, signed=True, granularity="layer", range={"name": "maminmax"},
+                 flag="weight", n_channels=1, dim=4):
+        super().__init__()
+        self.n_bits, self.symmetric, self.signed, self.granularity = n_bits, symmetric, signed, granularity
+        self.flag, self.n_channels, self.dim = flag, n_channels, dim
+        range = deepcopy(dict(range))
+        self.range = range.pop("name")
+        self.range_estimator = RANGES[self.range](n_bits=n_bits, symmetric=symmetric, signed=signed,
+                                                  granularity=granularity, **range)
+        if granularity in ("L", "Layer", "layer"):
+            self.n_channels = 1
+        self.scale = nn.Parameter(torch.ones(self.n_channels).view(*self.shape))
+        self.zero = nn.Parameter(torch.zeros(self.n_channels).view(*self.shape))
+        self.register_buffer("qmin", torch.tensor(-(2 ** (n_bits - 1))))
+        self.register_buffer("qmax", torch.tensor(2 ** (n_bits - 1) - 1))
+        self.quantized = False
+        self.packed = False
+
+    @property
+    def shape(self):                                                # quantizer.py:137-144
+        shape = [1] * self.dim
+        shape[1 if self.flag == "activation" else 0] = -1
+        return shape
+
+    def quant(self, quantized=True):
+        self.quantized = bool(quantized)
+
+    def quantize_int(self, x: Tensor) -> Tensor:                    # quantizer.py:31 + :215
+        return (x / self.scale.view(*self.shape) - self.zero.view(*self.shape)).round().clamp(self.qmin, self.qmax)
+
+    def simulate(self, x: Tensor):                                  # quantizer.py:196-226
+        self.dim = x.dim()
+        scale, zero = self.scale.view(*self.shape), self.zero.view(*self.shape)
+        q = self.quantize_int(x)
+        if not self.packed:
+            return (q + zero).mul(scale)
+        return q, scale, zero
+
+    def pack(self, x):                                              # quantizer.py:228-246
+        self.packed = True
+        if self.flag == "weight":
+            return self.quantize_int(x), self.scale.detach().clone(), self.zero.detach().clone()
+        return x, None, None
+
+    @torch.no_grad()
+    def calibrate(self, x: Tensor):                                 # quantizer.py:248-263
+        device = self.scale.device
+        scale, zero, qmin, qmax = self.range_estimator(self.flag, x)
+        self.scale.data = scale.view(*self.shape).to(device)
+        self.zero.data = zero.view(*self.shape).to(device)
+        self.qmin.copy_(torch.tensor(qmin).to(device))
+        self.qmax.copy_(torch.tensor(qmax).to(device))
+
+    def forward(self, x: Tensor):                                   # quantizer.py:265-279
+        if not self.quantized or self.n_bits >= 32:
+            return x
+        return self.simulate(x)
+
+
+DEFAULT_W = dict(n_bits=8, symmetric=True, signed=True, granularity="channel", range={"name": "minmax", "percentile": 0.0})
+DEFAULT_A = dict(n_bits=8, symmetric=False, granularity="layer", range={"name": "maminmax", "percentile": 0.0, "momentum": 0.1})
+# = the reference's configs/runners/ptq/minmax/base.yaml:1-19
+
+
+class QuantConv2d(nn.Conv2d):
+    """reference modelzoo/modules/quantconv2d.py:20-235, packed forward routed through the engine."""
+
+    def __init__(self, conv: nn.Conv2d, bn: nn.BatchNorm2d = None, w_setting=None, a_setting=None):
+        super().__init__(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                         conv.dilation, conv.groups, conv.bias is not None or bn is not None, conv.padding_mode)
+        assert conv.padding_mode == "zeros" and conv.dilation == (1, 1), "the op has no dilation / padding modes"
+        assert conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1], \
+            "the op takes one stride and one padding (quantconv2dop.py:82-85)"
+        w = conv.weight.detach().clone()
+        b = conv.bias.detach().clone() if conv.bias is not None else (torch.zeros(conv.out_channels) if bn is not None else None)
+        if bn is not None:                                          # quantconv2d.py:115-128 (bn_folding)
+            std = torch.sqrt(bn.running_var + bn.eps)
+            b = bn.bias.detach() + (b - bn.running_mean) * bn.weight.detach() / std   # same operation order as :117-121
+            w = w * (bn.weight.detach() / std).reshape(-1, 1, 1, 1)                   # :124-128
+        self.weight.data = w
+        if b is not None:
+            self.bias.data = b.reshape(-1)
+        self.w_quantizer = Quantizer(**(w_setting or DEFAULT_W), flag="weight", n_channels=conv.out_channels, dim=4)
+        self.a_quantizer = Quantizer(**(a_setting or DEFAULT_A), flag="activation", n_channels=conv.in_channels, dim=4)
+        self.calibrating = False
+        self.packed = False
+        self.use_engine = True
+
+    def calibrate(self, x: Tensor):                                 # quantconv2d.py:141-152
+        self.a_quantizer.calibrate(x.detach().clone())
+        self.w_quantizer.calibrate(self.weight.detach().clone())
+
+    def _forward(self, x: Tensor) -> Tensor:                        # quantconv2d.py:154-168
+        if self.calibrating:
+            self.calibrate(x)
+        x = self.a_quantizer(x)
+        weight = self.w_quantizer(self.weight)
+        return self._conv_forward(x, weight, self.bias)
+
+    @torch.no_grad()
+    def pack(self):                                                 # quantconv2d.py:170-196
+        self.requires_grad_(False)
+        self.a_quantizer.pack(None)
+        weight, w_scale, w_zero = self.w_quantizer.pack(self.weight)
+        self.register_buffer("w_scale", w_scale)
+        self.register_buffer("w_zero", w_zero)
+        qe = _engine.load()
+        self.weight.data, w_des = qe.tpack(weight.contiguous(), self.w_quantizer.n_bits, self.w_quantizer.signed)
+        self.register_buffer("w_des", w_des)
+        self.w_quantizer = None
+        self.packed = True
+
+    def forward(self, x: Tensor) -> Tensor:                         # quantconv2d.py:198-210
+        if not self.packed:
+            return self._forward(x)
+        a = self.a_quantizer
+        if self.use_engine:
+            return _engine.load().quantconv2d_float_input(
+                x.contiguous(), self.weight, self.w_des, self.w_scale, self.w_zero, self.bias, self.stride[0],
+                self.padding[0], input_scale=a.scale, input_zero=a.zero, input_qmin=a.qmin, input_qmax=a.qmax)
+        # the reference's packed forward, kept for cross-checks: float conv on dequantized operands
+        q, a_scale, a_zero = a.simulate(x)
+        w = _engine.load().tunpack(self.weight, self.w_des)
+        return self._conv_forward((q + a_zero).mul_(a_scale), (w + self.w_zero).mul_(self.w_scale), self.bias)
+
+
+def reconstruct(model: nn.Module, w_setting=None, a_setting=None) -> nn.Module:
+    """reference modelzoo/reconstruct.py:15-41, :94-132 for Conv2d(+BatchNorm2d): a conv directly followed (in
+    child order) by a BatchNorm2d is folded and the BN becomes Identity; other children are visited recursively.
+    nn.Linear layers are left in floating point (QuantLinear is off the hot path)."""
+    names = [n for n, _ in model.named_children()]
+    mods = dict(model.named_children())
+    skip = set()
+    for i, name in enumerate(names):
+        m = mods[name]
+        if name in skip:
+            setattr(model, name, nn.Identity())
+            continue
+        if isinstance(m, nn.Conv2d) and not isinstance(m, QuantConv2d):
+            nxt = mods[names[i + 1]] if i + 1 < len(names) else None
+            if isinstance(nxt, nn.BatchNorm2d):
+                setattr(model, name, QuantConv2d(m, nxt, w_setting, a_setting))
+                skip.add(names[i + 1])
+            else:
+                setattr(model, name, QuantConv2d(m, None, w_setting, a_setting))
+        else:
+            reconstruct(m, w_setting, a_setting)
+    return model
+
+
+def quant_layers(model):
+    return [m for m in model.modules() if isinstance(m, QuantConv2d)]
+
+
+def set_mode(model, calibrating=False, quantized=False):
+    """reference runner/ptq.py:51-63."""
+    model.train(False)
+    for m in model.modules():
+        if hasattr(m, "calibrating"):
+            m.calibrating = calibrating
+        if isinstance(m, Quantizer):
+            m.quant(quantized)
+
+
+@torch.no_grad()
+def calibrate(model, batch):
+    """one PTQ calibration pass (runner/ptq.py:70-78 with the modules in calibrating mode)."""
+    set_mode(model, calibrating=True, quantized=False)
+    model(batch)
+    set_mode(model, calibrating=False, quantized=True)
+
+
+def pack(model):
+    """the packing loop the reference keeps commented out (runner/ptq.py:106-114)."""
+    for m in quant_layers(model):
+        m.pack()
+    return model

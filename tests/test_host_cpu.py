@@ -1,0 +1,115 @@
+"""CPU: the host-side mirror (quantize_b200/host.py) against the reference's own modules (container only) and
+its calibration arithmetic against the committed fixtures."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+import refshim
+from quantize_b200 import host, models
+
+needs_ref = pytest.mark.skipif(not refshim.available(), reason="/root/reference not present (GPU box)")
+
+
+def _conv_bn(C, K, k, stride, pad, groups=1, seed=0):
+    torch.manual_seed(seed)
+    conv = nn.Conv2d(C, K, k, stride, pad, groups=groups, bias=False)
+    bn = nn.BatchNorm2d(K)
+    with torch.no_grad():
+        bn.running_mean.copy_(torch.randn(K))
+        bn.running_var.copy_(torch.rand(K) * 1.5 + 0.5)
+        bn.weight.copy_(1 + 0.2 * torch.randn(K))
+        bn.bias.copy_(torch.randn(K))
+    return conv, bn.eval()
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", [(16, 24, 3, 1, 1, 1, 8, 8), (8, 8, 3, 2, 1, 8, 4, 8), (12, 20, 1, 1, 0, 1, 4, 4)])
+def test_layer_mirror_is_bit_identical_to_reference_module(cfg):
+    C, K, k, stride, pad, groups, wb, ab = cfg
+    mods = refshim.load_reference(refshim.oracle_engine_module())
+    conv, bn = _conv_bn(C, K, k, stride, pad, groups)
+    w_setting = dict(host.DEFAULT_W, n_bits=wb)
+    a_setting = dict(host.DEFAULT_A, n_bits=ab)
+    mine = host.QuantConv2d(conv, bn, w_setting, a_setting)
+    ref = mods.QuantConv2d(C, K, k, stride, pad, 1, groups, w_setting=w_setting, a_setting=a_setting,
+                           bn_folding=dict(running_mean=bn.running_mean, running_var=bn.running_var, weight=bn.weight.detach(),
+                                           bias=bn.bias.detach(), eps=bn.eps),
+                           _parameters={"weight": conv.weight.detach().clone(), "bias": None})
+    assert torch.equal(mine.weight, ref.weight) and torch.equal(mine.bias, ref.bias)     # BN folding
+    x1, x2 = torch.randn(2, C, 9, 9), torch.randn(2, C, 9, 9) * 2
+    with torch.no_grad():
+        for m in (mine, ref):
+            m.calibrating = True
+            m.w_quantizer.quant(False); m.a_quantizer.quant(False)
+            m(x1); m(x2)                      # two batches: exercises the moving-average update
+            m.calibrating = False
+            m.w_quantizer.quant(True); m.a_quantizer.quant(True)
+        for q in ("a_quantizer", "w_quantizer"):
+            for p in ("scale", "zero", "qmin", "qmax"):
+                assert torch.equal(getattr(getattr(mine, q), p), getattr(getattr(ref, q), p)), (q, p)
+        assert torch.equal(mine(x1), ref(x1))                                            # fake-quant forward
+        wi, ws, wz = mine.w_quantizer.pack(mine.weight)
+        ri, rs, rz = ref.w_quantizer.pack(ref.weight)
+        assert torch.equal(wi, ri) and torch.equal(ws, rs) and torch.equal(wz, rz)       # integers handed to tpack
+
+
+@needs_ref
+def test_resnet20_reconstruct_matches_reference_reconstruct():
+    refshim.load_reference(refshim.oracle_engine_module())
+    from modelzoo.reconstruct import reconstruct as ref_reconstruct
+    from utils import Configs
+    import os
+    cfg = Configs()
+    cfg.merge_from_yaml(os.path.join(refshim.REF_ROOT, "configs/runners/ptq/minmax/base.yaml"))
+    cfg.freeze()
+    torch.manual_seed(0)
+    float_model = models.ResNet20()
+    with torch.no_grad():
+        models.perturb_bn(float_model, torch.Generator().manual_seed(1))
+    float_model.eval()
+    import copy
+    ref_model = ref_reconstruct(copy.deepcopy(float_model), cfg.quant)
+    # the reference also quantizes nn.Linear (QuantLinear, off the hot path): put the float FC back for the comparison
+    ref_model.fc = copy.deepcopy(float_model.fc)
+    mine = host.reconstruct(copy.deepcopy(float_model))
+    assert len(host.quant_layers(mine)) == 21
+    x = torch.randn(4, 3, 32, 32)
+    with torch.no_grad():
+        host.calibrate(mine, x)
+        for m in ref_model.modules():            # runner/ptq.py:51-63
+            if hasattr(m, "calibrating"):
+                m.calibrating = True
+            if m.__class__.__name__ == "Quantizer":
+                m.quant(False)
+        ref_model(x)
+        for m in ref_model.modules():
+            if hasattr(m, "calibrating"):
+                m.calibrating = False
+            if m.__class__.__name__ == "Quantizer":
+                m.quant(True)
+        assert torch.equal(mine(x), ref_model(x))
+
+
+def test_calibration_matches_fixture_parameters():
+    """MinMax / MAMinMax arithmetic against the parameters the reference produced for the committed fixtures."""
+    from conftest import load_conv_fixture
+    f = load_conv_fixture("w8a8_k3s1p1_neg")
+    q = host.Quantizer(**host.DEFAULT_A, flag="activation", n_channels=16, dim=4)
+    q.calibrate(torch.from_numpy(f["x"]))
+    assert np.array_equal(q.scale.detach().numpy().reshape(-1), f["a_scale"])
+    assert np.array_equal(q.zero.detach().numpy().reshape(-1), f["a_zero"])
+    assert float(q.qmin) == f["qmin"][0] and float(q.qmax) == f["qmax"][0]
+    q.quant(True)
+    assert np.array_equal(q.quantize_int(torch.from_numpy(f["x"])).detach().numpy().astype(np.uint8), f["q_x"])
+
+
+def test_conv_specs_and_work_match_survey():
+    specs = models.conv_layer_specs("resnet50", 256)
+    ops, nbytes = models.conv_stack_work(specs)
+    assert len(specs) == 53
+    assert abs(ops / 256 / 1e9 - 8.1743) < 1e-3          # 8.1743 Gop / image
+    assert abs(nbytes / 1e9 - 22.32) < 0.01              # 22.32 GB / batch-256 under the op contract
+    assert not specs[0]["relu_input"] and all(s["relu_input"] for s in specs[1:])
+    ops18, _ = models.conv_stack_work(models.conv_layer_specs("resnet18", 128))
+    assert abs(ops18 / 128 / 1e9 - 3.6271) < 1e-3

@@ -1,0 +1,90 @@
+"""GPU: whole networks of BASELINE.json's configs — packed inference through the engine vs the fake-quant path
+(the restated reference `_forward`, torch fp32 on the same GPU, TF32 off).  Bar: logits within 1e-3 relative of the
+logit scale, top-1 agreement 100 % on the synthetic batch."""
+import copy
+
+import pytest
+import torch
+
+from quantize_b200 import host, models
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def _compare(name, batch, w_bits, a_bits):
+    dev = "cuda"
+    model = models.build_quantized(name, w_bits, a_bits).to(dev)
+    x = models.synthetic_batch(name, batch, device=dev)
+    host.calibrate(model, x)
+    with torch.no_grad():
+        ref = model(x).clone()                       # fake-quant forward (quantconv2d.py:154-168)
+    packed = host.pack(copy.deepcopy(model))
+    with torch.no_grad():
+        out = packed(x)
+        for m in host.quant_layers(packed):
+            m.use_engine = False                     # the reference's packed forward: float conv on dequantized operands
+        out_ref_packed = packed(x)
+    scale = ref.abs().max()
+    assert (out - ref).abs().max() <= 1e-3 * scale, float((out - ref).abs().max() / scale)
+    assert (out - out_ref_packed).abs().max() <= 1e-3 * scale
+    assert torch.equal(out.argmax(1), ref.argmax(1))           # top-1 agreement 100 %
+    return out
+
+
+def test_resnet20_cifar_w8a8():
+    _compare("resnet20", 32, 8, 8)
+
+
+def test_resnet18_w8a8():
+    _compare("resnet18", 8, 8, 8)
+
+
+def test_resnet50_w8a8():
+    _compare("resnet50", 4, 8, 8)
+
+
+def test_resnet18_w4a4():
+    _compare("resnet18", 4, 4, 4)
+
+
+def test_mobilenet_v2_w4a8_depthwise_and_pointwise():
+    _compare("mobilenet_v2", 4, 4, 8)
+
+
+def test_batch_shards_equal_full_batch():
+    """rows [k*B/G, (k+1)*B/G) of the full batch == the shard run on its own (bit-for-bit)."""
+    model = models.build_packed("resnet18", 8, 8, calib_batch=4)
+    x = models.synthetic_batch("resnet18", 8, device="cuda")
+    with torch.no_grad():
+        full = model(x)
+        parts = [model(x[i:i + 2].contiguous()) for i in range(0, 8, 2)]
+    assert torch.equal(full, torch.cat(parts))
+
+
+def test_state_dict_round_trip_keeps_reference_format():
+    """packed weights are the reference's byte stream + w_des (quantconv2d.py:186-191) and survive a checkpoint."""
+    import io
+    model = models.build_packed("resnet20", 8, 8, calib_batch=4)
+    x = models.synthetic_batch("resnet20", 4, device="cuda")
+    with torch.no_grad():
+        want = model(x)
+    buf = io.BytesIO()
+    torch.save(model.state_dict(), buf)
+    buf.seek(0)
+    sd = torch.load(buf)
+    l0 = host.quant_layers(model)[0]
+    assert l0.weight.dtype == torch.uint8 and l0.weight.dim() == 1
+    assert l0.w_des.tolist() == [8, 1, 16, 3, 3, 3]
+    fresh = models.build_quantized("resnet20", 8, 8).to("cuda")
+    host.set_mode(fresh, quantized=True)
+    host.pack(fresh)
+    fresh.load_state_dict(sd)
+    with torch.no_grad():
+        assert torch.equal(fresh(x), want)
