@@ -197,6 +197,8 @@ class ConvStack:
         L, capi = self.L, self.capi
         for i, l in enumerate(self.layers):
             s = l["spec"]
+            if events is not None:
+                events[i][2].record()
             capi.check(L.qb200_act_quantize_nhwc(l["x"].data_ptr(), s["N"], s["C"], s["H"], s["W"], ctypes.byref(l["aq"]),
                                                  self.ws.data_ptr(), stream), "act_quantize")
             if events is not None:
@@ -245,8 +247,7 @@ def run_b200(args):
         stack.step(stream)
     K = args.steps
     nl = len(stack.layers)
-    events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
-              for _ in range(K)]
+    events = [[tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(nl)] for _ in range(K)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     barrier()
@@ -261,6 +262,7 @@ def run_b200(args):
     clocks = sampler.stop()
     ms = t0.elapsed_time(t1)
     conv_ms = [sum(events[k][i][0].elapsed_time(events[k][i][1]) for k in range(K)) / K for i in range(nl)]
+    quant_ms = [sum(events[k][i][2].elapsed_time(events[k][i][0]) for k in range(K)) / K for i in range(nl)]
     if world > 1:
         t = torch.tensor([ms], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -288,6 +290,8 @@ def run_b200(args):
                 "bytes_per_launch": round(conv_bytes / nl), "us_per_launch": round(conv_total_ms / nl * 1e3, 2),
                 "launches_per_step": nl,
                 "conv_share_of_step": round(conv_total_ms / ms_per_step, 4),
+                "act_quantize_share_of_step": round(sum(quant_ms) / ms_per_step, 4),
+                "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (sum(quant_ms) * 1e-3) / 1e9, 1),
                 "tensor_tops": round(total_ops / (conv_total_ms * 1e-3) / 1e12, 1),
                 "tensor_frac_of_int8_spec": round(total_ops / (conv_total_ms * 1e-3) / 1e12 / INT8_PEAK_TOPS, 4),
                 "step_contract_gbs": round(contract_bytes / (ms_per_step * 1e-3) / 1e9, 1),
@@ -295,8 +299,9 @@ def run_b200(args):
     if args.per_layer and rank == 0:
         for i, l in enumerate(stack.layers):
             s = l["spec"]
-            print(f"layer {i:2d} C{s['C']:4d} H{s['H']:3d} K{s['K']:4d} R{s['R']} s{s['stride']} conv {conv_ms[i]*1e3:8.1f} us "
-                  f"{l['conv_bytes']/conv_ms[i]/1e6:7.0f} GB/s {l['ops']/conv_ms[i]/1e9:7.0f} TOPS", file=sys.stderr)
+            print(f"layer {i:2d} C{s['C']:4d} H{s['H']:3d} K{s['K']:4d} R{s['R']} s{s['stride']} quant {quant_ms[i]*1e3:7.1f} us "
+                  f"{l['quant_bytes']/quant_ms[i]/1e6:6.0f} GB/s | conv {conv_ms[i]*1e3:7.1f} us "
+                  f"{l['conv_bytes']/conv_ms[i]/1e6:6.0f} GB/s {l['ops']/conv_ms[i]/1e9:6.0f} TOPS", file=sys.stderr)
 
     # ---- end to end through the public op API: host images -> logits on host ----------------------------
     e2e = None

@@ -6,41 +6,184 @@
 // and changes the layout to channel-last so that the implicit-GEMM conv can fetch K-contiguous im2col
 // rows with TMA.  Channels C..Cp-1 are written as 0 (they meet zero weights in the MMA).
 //
-// Machine mapping: one thread owns one pixel (n,h,w flattened), so every fp32 load is coalesced along
-// the pixel dimension (the contiguous one in NCHW); 16 channels are quantized into one 16-byte register
-// vector, staged in an XOR-swizzled shared tile of 128 pixels x 128 channel-bytes, and the tile is
-// written out as whole contiguous NHWC rows (128-byte lines when Cp >= 128).
-// HBM-bound: algorithmic bytes per element = 4 (read) + Cp/C (write).
+// Bit-exactness without paying an IEEE division per element: t' = fma(x, 1/scale, -zero) differs from the
+// reference's fl(fl(x/scale) - zero) by at most (|t| + |zero| + 1) * 2^-22, so rint(t') == rint(t) unless t' lies
+// within that margin of a rounding boundary (k + 0.5); only those elements (about 1 in 10^4) — and NaN / huge
+// values — take the exact divide.  tests/test_conv_gpu.py checks the integers against the oracle bit for bit.
+//
+// Machine mapping (vector kernel, H*W % 4 == 0): a block is 128 consecutive pixels; a thread owns 4 consecutive
+// pixels x 16 channels: 16 coalesced 16-byte loads (a warp reads 512 contiguous bytes of one channel plane),
+// quantizes in registers, writes four 16-byte channel vectors into an XOR-swizzled shared tile, and the block
+// copies the tile out as whole contiguous NHWC rows.  HBM-bound: bytes per element = 4 (read) + Cp/C (write).
 #include "common.cuh"
 
 namespace qb200 {
 namespace {
 
-constexpr int kPix = 128;  // pixels per block == threads per block
-constexpr int kCw = 128;   // channel bytes per pass
+constexpr int kPix = 128;  // pixels per block
+constexpr int kThreads = 128;
+constexpr int kCw = 128;   // channel bytes per shared-memory pass
 
-__device__ __forceinline__ uint32_t quant1(float x, float s, float z, float lo, float hi) {
+struct QuantParams {
+    float s, z, lo, hi;  // the reference's parameters
+    float r, nz, thr;    // 1/s, -z, fast-path threshold on |t' - rint(t')|
+    uint32_t lo4, hi4;   // qmin / qmax replicated into 4 bytes (valid when fast_clamp)
+    int fast_clamp;      // 0 <= qmin <= qmax <= 255 and both integral
+};
+
+__device__ __forceinline__ QuantParams load_params(const float* p_scale, const float* p_zero, const float* p_qmin,
+                                                   const float* p_qmax) {
+    QuantParams p;
+    p.s = __ldg(p_scale);
+    p.z = __ldg(p_zero);
+    p.lo = __ldg(p_qmin);
+    p.hi = __ldg(p_qmax);
+    p.r = __frcp_rn(p.s);
+    p.nz = -p.z;
+    const float maxq = fmaxf(fabsf(p.lo), fabsf(p.hi)) + 1.f;
+    p.thr = 0.5f - (maxq + fabsf(p.z) + 1.f) * 4.76837158203125e-7f;  // 2^-21
+    p.fast_clamp = (p.lo >= 0.f && p.hi <= 255.f && p.lo <= p.hi && p.lo == rintf(p.lo) && p.hi == rintf(p.hi)) ? 1 : 0;
+    const uint32_t l = (uint32_t)(int)fminf(fmaxf(p.lo, 0.f), 255.f), h = (uint32_t)(int)fminf(fmaxf(p.hi, 0.f), 255.f);
+    p.lo4 = l * 0x01010101u;
+    p.hi4 = h * 0x01010101u;
+    return p;
+}
+
+// the reference's arithmetic, verbatim (result already clamped)
+__device__ __noinline__ int quant_exact(float x, float s, float z, float lo, float hi) {
     float t = __fsub_rn(__fdiv_rn(x, s), z);  // x / scale - zero, no contraction
     t = rintf(t);                             // torch.round: half to even
-    t = fminf(fmaxf(t, lo), hi);              // clamp(qmin, qmax); NaN -> lo like torch.clamp? (see note)
-    return (uint32_t)(int)t & 0xFFu;
+    t = fminf(fmaxf(t, lo), hi);              // clamp(qmin, qmax); a NaN activation maps to qmin
+    return (int)t;
 }
-// note: torch.clamp propagates NaN; a NaN activation has no uint8 image, the reference would produce a NaN
-// output.  The kernel maps NaN to qmin; NaN inputs are outside the contract of a calibrated quantizer.
 
-__global__ void __launch_bounds__(kPix)
+// unclamped rint(x/s - z) for values whose clamped image is decided safely; exact path otherwise
+__device__ __forceinline__ int quant_int(float x, const QuantParams& p) {
+    const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest-even integer in the low mantissa bits
+    const float t = __fmaf_rn(x, p.r, p.nz);
+    const float u = __fadd_rn(t, magic);
+    const float d = fabsf(__fsub_rn(t, __fsub_rn(u, magic)));
+    int qi = __float_as_int(u) - 0x4B400000;
+    if (!(d < p.thr && fabsf(t) < 2097152.f)) qi = quant_exact(x, p.s, p.z, p.lo, p.hi);
+    return qi;
+}
+
+// four quantized values -> one little-endian word of u8, clamped to [qmin, qmax]
+__device__ __forceinline__ uint32_t pack4(int q0, int q1, int q2, int q3, const QuantParams& p) {
+    if (p.fast_clamp) {
+        uint32_t hi16, w;
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(q3), "r"(q2), "r"(0));
+        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q1), "r"(q0), "r"(hi16));
+        return __vminu4(__vmaxu4(w, p.lo4), p.hi4);
+    }
+    const int lo = (int)p.lo, hi = (int)p.hi;
+    q0 = min(max(q0, lo), hi);
+    q1 = min(max(q1, lo), hi);
+    q2 = min(max(q2, lo), hi);
+    q3 = min(max(q3, lo), hi);
+    return (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+}
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ void copy_out(const uint4* tile, uint8_t* __restrict__ q, int64_t g0, int n_rows, int chunks, int Cp,
+                                         int c_base) {
+    // rows of `chunks` 16-byte vectors at stride Cp; consecutive threads take consecutive vectors (full lines)
+    const int total = n_rows * chunks;
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+        const int row = i / chunks, col = i - row * chunks;
+        const uint4 v = tile[row * (kCw / 16) + (col ^ (row & 7))];
+        *reinterpret_cast<uint4*>(q + (g0 + row) * (int64_t)Cp + c_base + col * 16) = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// vector kernel: H*W % 4 == 0, x 16-byte aligned.  thread = (pixel quad, 16-channel group)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C, int Cp, int HW,
+                              const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                              const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    __shared__ uint4 tile[kPix * (kCw / 16)];
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int pq = threadIdx.x & 31;   // pixel quad inside the block
+    const int cg = threadIdx.x >> 5;   // 16-channel group inside a 64-channel sub-pass (warp-uniform)
+    const int64_t g0 = (int64_t)blockIdx.x * kPix;
+    const int64_t g = g0 + pq * 4;
+    const int c_base = blockIdx.y * kCw;
+    const int cw = min(kCw, Cp - c_base);  // multiple of 32
+    const int chunks = cw >> 4;
+
+    const bool active = g < total_pix;  // total_pix % 4 == 0: a quad is all-in or all-out, and never straddles images
+    const int64_t n = active ? g / HW : 0;
+    const int pix = (int)(g - n * HW);
+    for (int sub = 0; sub < chunks; sub += 4) {     // 64 channels per sub-pass
+        const int j = sub + cg;                      // this warp's 16-channel chunk
+        if (active && j < chunks) {
+            const int c0 = c_base + j * 16;
+            const float* xp = x + (n * C + c0) * (int64_t)HW + pix;
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < C) ? ldg_stream4(xp + (int64_t)i * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t w[4][4];  // [pixel][word]
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int a[4][4];   // [pixel][channel in word]
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int i = k * 4 + b;
+                    const bool ok = c0 + i < C;
+                    a[0][b] = ok ? quant_int(v[i].x, p) : 0;
+                    a[1][b] = ok ? quant_int(v[i].y, p) : 0;
+                    a[2][b] = ok ? quant_int(v[i].z, p) : 0;
+                    a[3][b] = ok ? quant_int(v[i].w, p) : 0;
+                }
+#pragma unroll
+                for (int px = 0; px < 4; ++px) w[px][k] = pack4(a[px][0], a[px][1], a[px][2], a[px][3], p);
+            }
+            // padded channels must be exactly 0 even when qmin > 0
+            if (c0 + 16 > C) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c0 + k * 4 + b < C) keep |= 0xFFu << (8 * b);
+#pragma unroll
+                    for (int px = 0; px < 4; ++px) w[px][k] &= keep;
+                }
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                const int row = pq * 4 + px;
+                tile[row * (kCw / 16) + (j ^ (row & 7))] = make_uint4(w[px][0], w[px][1], w[px][2], w[px][3]);
+            }
+        }
+    }
+    __syncthreads();
+    const int n_rows = (int)min((int64_t)kPix, total_pix - g0);
+    copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernel: any H*W / alignment.  thread = one pixel, scalar (still warp-coalesced) loads
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
 act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C,
                          int Cp, int HW, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                          const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
     __shared__ uint4 tile[kPix * (kCw / 16)];
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
     const int t = threadIdx.x;
     const int64_t g0 = (int64_t)blockIdx.x * kPix;
     const int64_t g = g0 + t;
     const int c_base = blockIdx.y * kCw;
     const int cw = min(kCw, Cp - c_base);  // multiple of 32
     const int chunks = cw >> 4;
-
-    const float s = __ldg(p_scale), z = __ldg(p_zero), lo = __ldg(p_qmin), hi = __ldg(p_qmax);
 
     if (g < total_pix) {
         const int64_t n = g / HW;
@@ -54,27 +197,22 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
             uint32_t w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                uint32_t acc = 0;
+                int a[4];
+                uint32_t keep = 0;
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const int i = k * 4 + b;
-                    const uint32_t qv = (c0 + i < C) ? quant1(v[i], s, z, lo, hi) : 0u;
-                    acc |= qv << (8 * b);
+                    const bool ok = c0 + k * 4 + b < C;
+                    a[b] = ok ? quant_int(v[k * 4 + b], p) : 0;
+                    if (ok) keep |= 0xFFu << (8 * b);
                 }
-                w[k] = acc;
+                w[k] = pack4(a[0], a[1], a[2], a[3], p) & keep;
             }
             tile[t * (kCw / 16) + (j ^ (t & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
     __syncthreads();
-    // copy-out: rows of cw bytes at stride Cp; chunk index i -> (row, col)
     const int n_rows = (int)min((int64_t)kPix, total_pix - g0);
-    const int total_chunks = n_rows * chunks;
-    for (int i = t; i < total_chunks; i += kPix) {
-        const int row = i / chunks, col = i - row * chunks;
-        const uint4 v = tile[row * (kCw / 16) + (col ^ (row & 7))];
-        *reinterpret_cast<uint4*>(q + (g0 + row) * (int64_t)Cp + c_base + col * 16) = v;
-    }
+    copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
 }
 
 }  // namespace
@@ -94,10 +232,14 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
     QB_REQUIRE(x && q_nhwc, QB200_EINVAL, "act_quantize: null pointer");
     QB_REQUIRE(reinterpret_cast<uintptr_t>(q_nhwc) % 16 == 0, QB200_EINVAL, "act_quantize: output must be 16-B aligned");
     const int Cp = qb200_padded_channels(C);
-    const int64_t total = (int64_t)N * H * W;
+    const int HW = H * W;
+    const int64_t total = (int64_t)N * HW;
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((Cp + kCw - 1) / kCw));
-    act_quantize_nhwc_kernel<<<grid, kPix, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, q_nhwc, total, C, Cp, H * W, aq->scale, aq->zero, aq->qmin, aq->qmax);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
+        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, aq->scale, aq->zero, aq->qmin, aq->qmax);
+    else
+        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, aq->scale, aq->zero, aq->qmin, aq->qmax);
     QB_LAUNCH_CHECK();
     return 0;
 }

@@ -9,9 +9,12 @@
 //   B  = prepared weights [K][R][S][Cp] (K-major), fetched with a tiled 2-D TMA;
 //   D  = int32 accumulators in TMEM (tcgen05.mma.cta_group::1.kind::i8, u8 x s8 -> s32), double buffered so the
 //        epilogue of tile i overlaps the main loop of tile i+1.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (tcgen05.ld -> dequant -> coalesced NCHW stores: a TMEM lane is an output pixel, so the 32
-// lanes of a warp write 32 consecutive pixels of one output channel = one 128-byte line).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (tcgen05.ld -> dequant -> coalesced NCHW stores: a TMEM lane is an output pixel, so the 32
+// lanes of a warp write 32 consecutive pixels of one output channel = one 128-byte line).  The per-channel
+// constants (s_a*s_w[k], bias[k] + s_a*s_w[k]*z_a*sum(qw[k])) are staged in shared memory once per tile so that an
+// interior pixel costs one convert + one FMA + one store per output element; border pixels of a layer with a
+// non-zero activation zero point take the 4-corner prefix-sum path.
 // Persistent: grid = #SMs, static round-robin tile schedule, output-channel tiles fastest so concurrently
 // running CTAs share the same activation slice in L2.
 #include "common.cuh"
@@ -23,7 +26,10 @@ namespace qb200 {
 namespace {
 
 constexpr int kBM = 128;            // pixels per tile = TMEM lanes = UMMA M
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each owns half of the tile's columns
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
+constexpr int kTailBytes = 256 + 2 * kConstFloats * 4;  // barriers + two constant buffers
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
 constexpr int kMaxStages = 8;
@@ -133,6 +139,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (tcgen05): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
@@ -163,6 +181,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
     uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][3][256]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -178,7 +197,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_empty[i], kEpiWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -245,44 +264,96 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         // ===================== epilogue =====================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        const int e = warp - 2;
+        const int quad = warp & 3;   // TMEM lane quadrant this warp may read
+        const int half = e >> 2;     // which half of the tile's columns
+        const int et = threadIdx.x - 64;
         const int row = quad * 32 + lane;
         const int PQ = g.P * g.Q;
-        const EpilogueScalars es = load_epilogue_scalars(prm.ep);
-        int buf = 0;
+        const EpilogueParams& ep = prm.ep;
+        const EpilogueScalars es = load_epilogue_scalars(ep);
+        const bool acc_out = ep.out_kind == QB200_OUT_ACC;
+        const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
+        int buf = 0, iter = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int n_tile = tile % prm.n_tiles;
             const int m_tile = tile / prm.n_tiles;
+            const int k_base = n_tile * BN;
+            // ---- per-tile channel constants (once per CTA when there is a single channel tile) ----
+            float* sc = consts + (prm.n_tiles > 1 ? buf : 0) * kConstFloats;
+            float* be = sc + 256;
+            float* br = sc + 512;
+            if (iter == 0 || prm.n_tiles > 1) {
+                if (et < BN) {
+                    const int k = k_base + et;
+                    float scale = 0.f, bias = 0.f, beff = 0.f;
+                    if (k < g.K) {
+                        scale = __fmul_rn(es.s_a, __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k)));
+                        bias = ep.bias ? __ldg(ep.bias + k) : 0.f;
+                        beff = bias;
+                        if (es.z_a != 0.f) {
+                            const int32_t wfull = __ldg(ep.wpre + (int64_t)(k + 1) * (g.R + 1) * (g.S + 1) - 1);
+                            beff = __fmaf_rn(scale, __fmul_rn(es.z_a, (float)wfull), bias);
+                        }
+                    }
+                    sc[et] = scale;
+                    be[et] = beff;
+                    br[et] = bias;
+                }
+                epi_barrier();
+            }
             const int64_t m = (int64_t)m_tile * kBM + row;
             const bool row_ok = m < prm.M;
             const int img = row_ok ? (int)(m / PQ) : 0;
             const int pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
             const int p = pq / g.Q, q = pq - p * g.Q;
             const PixelWindow pw = pixel_window(g, p, q);
-            const int k_base = n_tile * BN;
+            const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
+            const bool full_n = k_base + BN <= g.K;
             const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
 
             mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride);
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(taddr + (uint32_t)c0, v);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride + half * cols);
+            for (int c0 = 0; c0 < cols; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
                 tmem_ld_wait();
-                if (row_ok) {
-                    if (prm.ep.out_kind == QB200_OUT_ACC) {
-                        int32_t* o = static_cast<int32_t*>(out) + o_base + (int64_t)c0 * PQ;
+                const int cc = half * cols + c0;  // first column of this chunk inside the tile
+                if (!row_ok) continue;
+                if (!acc_out && full_n && interior) {
+                    float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (k_base + c0 + j < g.K) o[(int64_t)j * PQ] = (int32_t)v[j];
-                    } else {
-                        float* o = static_cast<float*>(out) + o_base + (int64_t)c0 * PQ;
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+                        const float4 b4 = *reinterpret_cast<const float4*>(be + cc + j);
+                        o[0] = __fmaf_rn((float)(int32_t)v[j + 0], s4.x, b4.x);
+                        o[PQ] = __fmaf_rn((float)(int32_t)v[j + 1], s4.y, b4.y);
+                        o[2 * (int64_t)PQ] = __fmaf_rn((float)(int32_t)v[j + 2], s4.z, b4.z);
+                        o[3 * (int64_t)PQ] = __fmaf_rn((float)(int32_t)v[j + 3], s4.w, b4.w);
+                        o += 4 * (int64_t)PQ;
+                    }
+                } else if (acc_out) {
+                    int32_t* o = static_cast<int32_t*>(out) + o_base + (int64_t)cc * PQ;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int k = k_base + c0 + j;
-                            if (k < g.K) o[(int64_t)j * PQ] = dequant_one((int32_t)v[j], k, g, prm.ep, es, pw);
+                    for (int j = 0; j < 32; ++j)
+                        if (k_base + cc + j < g.K) o[(int64_t)j * PQ] = (int32_t)v[j];
+                } else {
+                    // ragged channel tile and / or border pixel of a layer with a non-zero activation zero point
+                    float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int k = k_base + cc + j;
+                        if (k >= g.K) continue;
+                        float r;
+                        if (interior) {
+                            r = __fmaf_rn((float)(int32_t)v[j], sc[cc + j], be[cc + j]);
+                        } else {
+                            const float t = __fmaf_rn(es.z_a, (float)window_wsum(ep.wpre, k, g.R, g.S, pw), (float)(int32_t)v[j]);
+                            r = __fmaf_rn(sc[cc + j], t, br[cc + j]);
                         }
+                        o[(int64_t)j * PQ] = r;
                     }
                 }
             }
@@ -395,7 +466,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.BN = BN;
     prm.n_tiles = (g.K + BN - 1) / BN;
     const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
-    int stages = (int)((kSmemBudget - 2048) / stage_bytes);
+    int stages = (int)((kSmemBudget - 1024 - kTailBytes) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
     prm.stages = stages;
@@ -437,11 +508,11 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + kTailBytes;
     static thread_local size_t smem_set = 0;
     if (smem > smem_set) {
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSmemBudget + 2048)));
-        smem_set = kSmemBudget + 2048;
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        smem_set = kSmemBudget;
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
     const int grid = total_tiles < sms ? total_tiles : sms;
