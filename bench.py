@@ -5,7 +5,7 @@
   torchrun --nproc-per-node N bench.py --gpus N ...               one process per GPU, weak scaling (256 images / GPU)
 
 A step = one pass of the hot path over one batch: the 53 convolutions of ResNet-50 at batch 256, every layer through
-qb200_act_quantize_nhwc + qb200_conv2d_q8_nhwc (the two kernels of quant_engine.quantconv2d_float_input's fused
+qb200_conv_quantize_input + qb200_conv_from_workspace (the two kernels of quant_engine.quantconv2d_float_input's fused
 path) on its own synthetic fp32 NCHW input that is resident in HBM when the timed region starts.
   value      images/s over all ranks, device-timed (CUDA events, max over ranks)
   e2e        the same metric through the public API a user calls — the packed ResNet-50 built from host.QuantConv2d
@@ -199,13 +199,13 @@ class ConvStack:
             s = l["spec"]
             if events is not None:
                 events[i][2].record()
-            capi.check(L.qb200_act_quantize_nhwc(l["x"].data_ptr(), s["N"], s["C"], s["H"], s["W"], ctypes.byref(l["aq"]),
-                                                 self.ws.data_ptr(), stream), "act_quantize")
+            capi.check(L.qb200_conv_quantize_input(ctypes.byref(l["shape"]), l["x"].data_ptr(), ctypes.byref(l["aq"]),
+                                                   self.ws.data_ptr(), stream), "quantize_input")
             if events is not None:
                 events[i][0].record()
-            capi.check(L.qb200_conv2d_q8_nhwc(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
-                                              l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(), ctypes.byref(l["aq"]),
-                                              self.out.data_ptr(), capi.OUT_F32, stream), "conv")
+            capi.check(L.qb200_conv_from_workspace(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
+                                                   l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
+                                                   ctypes.byref(l["aq"]), self.out.data_ptr(), capi.OUT_F32, stream), "conv")
             if events is not None:
                 events[i][1].record()
 

@@ -115,7 +115,7 @@ typedef struct {
     const float* qmax;
 } qb200_act_quant;
 
-/* workspace (bytes) the fused conv needs for the quantized NHWC activations: N*H*W*Cp */
+/* workspace (bytes) the fused conv needs for the quantized activations: N*H*W*Cp, or N*P*Q*Kcol for few-channel layers */
 size_t qb200_conv_workspace_bytes(const qb200_conv_shape* s);
 
 /* q = clamp(rint(x / scale - zero), qmin, qmax) as uint8, NCHW fp32 -> NHWC(Cp) u8, channels C..Cp-1 = 0
@@ -146,7 +146,16 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
                             const qb200_act_quant* aq, void* workspace, void* out, int32_t out_kind,
                             void* stream);
 
-/* Same conv on already-quantized NHWC(Cp) activations (the second half of the fused op). */
+/* The two kernels of the fused op as separate calls (same result as qb200_quantconv2d_fused; lets a caller time or
+ * overlap them).  The workspace layout is private to the pair: NHWC(Cp) bytes, or — for layers with <= 4 input
+ * channels such as the RGB stem — materialised im2col rows. */
+int qb200_conv_quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, void* workspace,
+                              void* stream);
+int qb200_conv_from_workspace(const qb200_conv_shape* s, const void* workspace, const void* prepared,
+                              const float* w_scale, int32_t n_w_scale, const float* bias, const qb200_act_quant* aq,
+                              void* out, int32_t out_kind, void* stream);
+
+/* Same conv on already-quantized NHWC(Cp) activations (callers that keep activations quantized). */
 int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared,
                          const float* w_scale, int32_t n_w_scale, const float* bias,
                          const qb200_act_quant* aq, void* out, int32_t out_kind, void* stream);

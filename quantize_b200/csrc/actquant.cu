@@ -16,6 +16,7 @@
 // quantizes in registers, writes four 16-byte channel vectors into an XOR-swizzled shared tile, and the block
 // copies the tile out as whole contiguous NHWC rows.  HBM-bound: bytes per element = 4 (read) + Cp/C (write).
 #include "common.cuh"
+#include "conv_common.cuh"
 
 namespace qb200 {
 namespace {
@@ -46,42 +47,46 @@ __device__ __forceinline__ QuantParams load_params(const float* p_scale, const f
     const uint32_t l = (uint32_t)(int)fminf(fmaxf(p.lo, 0.f), 255.f), h = (uint32_t)(int)fminf(fmaxf(p.hi, 0.f), 255.f);
     p.lo4 = l * 0x01010101u;
     p.hi4 = h * 0x01010101u;
+    if (!p.fast_clamp) p.thr = -1.f;  // quantizers outside [0, 255]: every word takes the exact path
     return p;
 }
 
-// the reference's arithmetic, verbatim (result already clamped)
-__device__ __noinline__ int quant_exact(float x, float s, float z, float lo, float hi) {
-    float t = __fsub_rn(__fdiv_rn(x, s), z);  // x / scale - zero, no contraction
-    t = rintf(t);                             // torch.round: half to even
-    t = fminf(fmaxf(t, lo), hi);              // clamp(qmin, qmax); a NaN activation maps to qmin
-    return (int)t;
-}
-
-// unclamped rint(x/s - z) for values whose clamped image is decided safely; exact path otherwise
-__device__ __forceinline__ int quant_int(float x, const QuantParams& p) {
-    const float magic = 12582912.f;  // 1.5 * 2^23: adding it rounds to the nearest-even integer in the low mantissa bits
-    const float t = __fmaf_rn(x, p.r, p.nz);
-    const float u = __fadd_rn(t, magic);
-    const float d = fabsf(__fsub_rn(t, __fsub_rn(u, magic)));
-    int qi = __float_as_int(u) - 0x4B400000;
-    if (!(d < p.thr && fabsf(t) < 2097152.f)) qi = quant_exact(x, p.s, p.z, p.lo, p.hi);
-    return qi;
-}
-
-// four quantized values -> one little-endian word of u8, clamped to [qmin, qmax]
-__device__ __forceinline__ uint32_t pack4(int q0, int q1, int q2, int q3, const QuantParams& p) {
-    if (p.fast_clamp) {
-        uint32_t hi16, w;
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(q3), "r"(q2), "r"(0));
-        asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q1), "r"(q0), "r"(hi16));
-        return __vminu4(__vmaxu4(w, p.lo4), p.hi4);
+// the reference's arithmetic, verbatim, for the four channels of one output word (results clamped)
+__device__ __noinline__ uint32_t quant_word_exact(float x0, float x1, float x2, float x3, float s, float z, float lo, float hi) {
+    const float xs[4] = {x0, x1, x2, x3};
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float t = __fsub_rn(__fdiv_rn(xs[i], s), z);  // x / scale - zero, no contraction
+        t = rintf(t);                                 // torch.round: half to even
+        t = fminf(fmaxf(t, lo), hi);                  // clamp(qmin, qmax); a NaN activation maps to qmin
+        w |= ((uint32_t)(int)t & 0xFFu) << (8 * i);
     }
-    const int lo = (int)p.lo, hi = (int)p.hi;
-    q0 = min(max(q0, lo), hi);
-    q1 = min(max(q1, lo), hi);
-    q2 = min(max(q2, lo), hi);
-    q3 = min(max(q3, lo), hi);
-    return (uint32_t)(q0 & 0xFF) | ((uint32_t)(q1 & 0xFF) << 8) | ((uint32_t)(q2 & 0xFF) << 16) | ((uint32_t)(q3 & 0xFF) << 24);
+    return w;
+}
+
+// One output word = four channels of one pixel.  Fast path: t' = fma(x, 1/s, -z); adding 1.5*2^23 rounds it to the
+// nearest-even integer in the low mantissa bits; it is trusted when t' is farther than the error bound from a
+// rounding boundary and small enough for the trick; saturating pack + byte-wise min/max do the clamp.  If any of
+// the four needs it (about 1 word in 10^3), the whole word is recomputed with the reference's exact arithmetic.
+__device__ __forceinline__ uint32_t quant_word(float x0, float x1, float x2, float x3, const QuantParams& p) {
+    const float magic = 12582912.f;
+    const float xs[4] = {x0, x1, x2, x3};
+    int q[4];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float t = __fmaf_rn(xs[i], p.r, p.nz);
+        const float u = __fadd_rn(t, magic);
+        const float d = fabsf(__fsub_rn(t, __fsub_rn(u, magic)));
+        q[i] = __float_as_int(u) - 0x4B400000;
+        ok = ok && (d < p.thr) && (fabsf(t) < 2097152.f);
+    }
+    if (!ok) return quant_word_exact(x0, x1, x2, x3, p.s, p.z, p.lo, p.hi);
+    uint32_t hi16, w;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(q[3]), "r"(q[2]), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q[1]), "r"(q[0]), "r"(hi16));
+    return __vminu4(__vmaxu4(w, p.lo4), p.hi4);
 }
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
@@ -127,23 +132,25 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
             const int c0 = c_base + j * 16;
             const float* xp = x + (n * C + c0) * (int64_t)HW + pix;
             float4 v[16];
+            if (c0 + 16 <= C) {   // warp-uniform: all 16 channel planes exist; walk the plane stride with pointer adds
+                const float* pi = xp;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < C) ? ldg_stream4(xp + (int64_t)i * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = ldg_stream4(pi);
+                    pi += HW;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    v[i] = (c0 + i < C) ? ldg_stream4(xp + (int64_t)i * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
             uint32_t w[4][4];  // [pixel][word]
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                int a[4][4];   // [pixel][channel in word]
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int i = k * 4 + b;
-                    const bool ok = c0 + i < C;
-                    a[0][b] = ok ? quant_int(v[i].x, p) : 0;
-                    a[1][b] = ok ? quant_int(v[i].y, p) : 0;
-                    a[2][b] = ok ? quant_int(v[i].z, p) : 0;
-                    a[3][b] = ok ? quant_int(v[i].w, p) : 0;
-                }
-#pragma unroll
-                for (int px = 0; px < 4; ++px) w[px][k] = pack4(a[px][0], a[px][1], a[px][2], a[px][3], p);
+                w[0][k] = quant_word(v[4 * k].x, v[4 * k + 1].x, v[4 * k + 2].x, v[4 * k + 3].x, p);
+                w[1][k] = quant_word(v[4 * k].y, v[4 * k + 1].y, v[4 * k + 2].y, v[4 * k + 3].y, p);
+                w[2][k] = quant_word(v[4 * k].z, v[4 * k + 1].z, v[4 * k + 2].z, v[4 * k + 3].z, p);
+                w[3][k] = quant_word(v[4 * k].w, v[4 * k + 1].w, v[4 * k + 2].w, v[4 * k + 3].w, p);
             }
             // padded channels must be exactly 0 even when qmin > 0
             if (c0 + 16 > C) {
@@ -197,15 +204,11 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
             uint32_t w[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                int a[4];
                 uint32_t keep = 0;
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const bool ok = c0 + k * 4 + b < C;
-                    a[b] = ok ? quant_int(v[k * 4 + b], p) : 0;
-                    if (ok) keep |= 0xFFu << (8 * b);
-                }
-                w[k] = pack4(a[0], a[1], a[2], a[3], p) & keep;
+                for (int b = 0; b < 4; ++b)
+                    if (c0 + k * 4 + b < C) keep |= 0xFFu << (8 * b);
+                w[k] = quant_word(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3], p) & keep;
             }
             tile[t * (kCw / 16) + (j ^ (t & 7))] = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -215,7 +218,76 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
     copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
 }
 
+// ---------------------------------------------------------------------------------------------
+// few-channel layers (RGB stem): quantize straight into im2col rows.
+// One block = one output row (n, p).  The R input rows it touches are quantized ONCE into a shared patch of packed
+// words (one word = the <=4 channels of a pixel); pixels outside the image are 0, so that padded taps add nothing to
+// sum(qa*qw) — the reference skips them (quantconv2d_float_input.cu:92) and their zero-point term is excluded by the
+// border tables.  Then every output pixel's row of Kcol bytes (word r*S+s = patch[r][q*stride + s], remaining words 0)
+// is written with fully coalesced stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+act_quantize_im2col_kernel(const float* __restrict__ x, uint32_t* __restrict__ a_col, ConvGeom g, int Kwords,
+                           const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                           const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    extern __shared__ uint32_t patch[];  // [R][Wp], Wp = W + 2*pad
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int Wp = g.W + 2 * g.pad;
+    const int n = blockIdx.x / g.P, po = blockIdx.x - n * g.P;
+    const int h0 = po * g.stride - g.pad;
+    const int HW = g.H * g.W;
+    for (int i = threadIdx.x; i < g.R * Wp; i += blockDim.x) {
+        const int r = i / Wp, j = i - r * Wp;
+        const int ih = h0 + r, iw = j - g.pad;
+        uint32_t word = 0;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+            const float* xp = x + (int64_t)n * g.C * HW + (int64_t)ih * g.W + iw;
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < g.C) a[c] = __ldg(xp + (int64_t)c * HW);
+            word = quant_word(a[0], a[1], a[2], a[3], p);
+            if (g.C < 4) word &= (1u << (8 * g.C)) - 1u;
+        }
+        patch[i] = word;
+    }
+    __syncthreads();
+    const int taps = g.R * g.S;
+    uint32_t* orow = a_col + ((int64_t)n * g.P + po) * g.Q * Kwords;
+    if (blockDim.x % Kwords == 0) {
+        // every thread owns one word position of the row for all the pixels it visits: no per-word division
+        const int wd = threadIdx.x % Kwords, q0 = threadIdx.x / Kwords, qstep = blockDim.x / Kwords;
+        const int r = wd / g.S;
+        const int off = (wd < taps) ? r * Wp + (wd - r * g.S) : -1;
+        for (int q = q0; q < g.Q; q += qstep) orow[q * Kwords + wd] = off >= 0 ? patch[off + q * g.stride] : 0u;
+    } else {
+        for (int i = threadIdx.x; i < g.Q * Kwords; i += blockDim.x) {
+            const int q = i / Kwords, wd = i - q * Kwords;
+            uint32_t v = 0;
+            if (wd < taps) {
+                const int r = wd / g.S, s = wd - r * g.S;
+                v = patch[r * Wp + q * g.stride + s];
+            }
+            orow[i] = v;
+        }
+    }
+}
+
 }  // namespace
+
+int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
+                               cudaStream_t st) {
+    QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL,
+               "act_quantize: activation quantizer parameters missing");
+    QB_REQUIRE(g.C <= 4 && g.groups == 1 && Kcol >= g.R * g.S * 4, QB200_EINVAL, "act_quantize_im2col: not a few-channel layer");
+    const size_t smem = (size_t)g.R * (g.W + 2 * g.pad) * sizeof(uint32_t);
+    QB_REQUIRE(smem <= 48 * 1024, QB200_EUNSUPPORTED, "act_quantize_im2col: input row too wide");
+    act_quantize_im2col_kernel<<<(unsigned)(g.N * g.P), 256, smem, st>>>(x, reinterpret_cast<uint32_t*>(a_col), g, Kcol / 4,
+                                                                         aq->scale, aq->zero, aq->qmin, aq->qmax);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace qb200
 
 extern "C" {

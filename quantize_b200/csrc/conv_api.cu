@@ -7,13 +7,30 @@ namespace {
 
 int g_conv_algo = QB200_ALGO_AUTO;
 
-int run_conv_q8(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared, const float* w_scale,
-                int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind,
-                cudaStream_t st) {
+int resolve_algo(const ConvGeom& g) {
+    int algo = g_conv_algo;
+    if (algo == QB200_ALGO_AUTO) algo = umma_supported(g) ? QB200_ALGO_UMMA : QB200_ALGO_DIRECT;
+    return algo;
+}
+
+// does the conv kernel chosen for this shape read materialised im2col rows (few-channel layers) or NHWC(Cp) bytes?
+bool workspace_is_im2col(const ConvGeom& g, const PreparedLayout& L) { return resolve_algo(g) == QB200_ALGO_UMMA && L.Kcol > 0; }
+
+int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, uint8_t* ws, cudaStream_t st) {
+    QB_REQUIRE(x && ws, QB200_EINVAL, "conv: null pointer");
+    const ConvGeom g = make_geom(*s);
+    const PreparedLayout L = prepared_layout(*s);
+    if (workspace_is_im2col(g, L)) return launch_act_quantize_im2col(x, g, L.Kcol, aq, ws, st);
+    return qb200_act_quantize_nhwc(x, s->N, s->C, s->H, s->W, aq, ws, st);
+}
+
+// from_ws: `q` is the workspace written by quantize_input (layout per workspace_is_im2col); else NHWC(Cp) bytes
+int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const void* prepared, const float* w_scale,
+             int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind, cudaStream_t st) {
     QB_REQUIRE(n_w_scale == 1 || n_w_scale == s->K, QB200_EINVAL, "weight_scale must have 1 or K elements");
     QB_REQUIRE(out_kind == QB200_OUT_F32 || out_kind == QB200_OUT_ACC, QB200_EINVAL, "conv: bad out_kind");
     QB_REQUIRE(aq && aq->scale && aq->zero, QB200_EINVAL, "conv: activation quantizer parameters missing");
-    QB_REQUIRE(q_nhwc && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
+    QB_REQUIRE(q && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
     const ConvGeom g = make_geom(*s);
     const PreparedLayout L = prepared_layout(*s);
     const uint8_t* wq = static_cast<const uint8_t*>(prepared);
@@ -25,11 +42,9 @@ int run_conv_q8(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* pr
     ep.wpre = reinterpret_cast<const int32_t*>(wq + L.wpre_off);
     ep.per_tensor_w = n_w_scale == 1;
     ep.out_kind = out_kind;
-
-    int algo = g_conv_algo;
-    if (algo == QB200_ALGO_AUTO) algo = umma_supported(g) ? QB200_ALGO_UMMA : QB200_ALGO_DIRECT;
-    if (algo == QB200_ALGO_UMMA) return launch_conv_umma(g, q_nhwc, wq, ep, out, st);
-    return launch_conv_direct(g, q_nhwc, wq, ep, out, st);
+    if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
+    if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(g, q, wq, ep, out, st);
+    return launch_conv_direct(g, q, wq, ep, out, st);
 }
 
 }  // namespace
@@ -46,7 +61,25 @@ int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const
     using namespace qb200;
     if (int rc = validate_shape(s)) return rc;
     if (s->N == 0) return 0;
-    return run_conv_q8(s, q_nhwc, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, static_cast<cudaStream_t>(stream));
+    return run_conv(s, q_nhwc, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, static_cast<cudaStream_t>(stream));
+}
+
+int qb200_conv_quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, void* workspace,
+                              void* stream) {
+    using namespace qb200;
+    if (int rc = validate_shape(s)) return rc;
+    if (s->N == 0) return 0;
+    return quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream));
+}
+
+int qb200_conv_from_workspace(const qb200_conv_shape* s, const void* workspace, const void* prepared, const float* w_scale,
+                              int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind,
+                              void* stream) {
+    using namespace qb200;
+    if (int rc = validate_shape(s)) return rc;
+    if (s->N == 0) return 0;
+    return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
@@ -56,9 +89,9 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
     if (int rc = validate_shape(s)) return rc;
     if (s->N == 0) return 0;
     QB_REQUIRE(workspace != nullptr, QB200_EINVAL, "conv: workspace missing (qb200_conv_workspace_bytes)");
-    if (int rc = qb200_act_quantize_nhwc(x, s->N, s->C, s->H, s->W, aq, static_cast<uint8_t*>(workspace), stream)) return rc;
-    return run_conv_q8(s, static_cast<const uint8_t*>(workspace), prepared, w_scale, n_w_scale, bias, aq, out, out_kind,
-                       static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (int rc = quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), st)) return rc;
+    return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st);
 }
 
 }  // extern "C"

@@ -13,8 +13,18 @@ struct PreparedLayout {
     int Cgp;
     size_t wq_bytes;
     size_t wpre_off;
+    int Kcol;          // bytes per row of the materialised-im2col weight matrix (0: layer does not use it)
+    size_t wcol_off;
     size_t total;
 };
+// Layers with very few input channels (the RGB stem) waste the tensor pipe and the TMA unit when channels are padded
+// to 32 per tap; for them the activation pass writes the im2col matrix itself (one 4-byte word per tap = the pixel's
+// <=4 channels) and the conv runs as a plain GEMM over Kcol "channels".
+static inline bool uses_im2col_rows(const qb200_conv_shape& s) { return s.C == s.Cg && s.C <= 4 && s.R * s.S > 1; }
+static inline int im2col_row_bytes(int R, int S) {
+    const int kq = R * S * 4;
+    return kq > 64 ? (kq + 127) / 128 * 128 : (kq > 32 ? 64 : 32);
+}
 PreparedLayout prepared_layout(const qb200_conv_shape& s);
 int validate_shape(const qb200_conv_shape* s);
 
@@ -87,8 +97,12 @@ __device__ __forceinline__ float dequant_one(int32_t acc, int k, const ConvGeom&
 
 int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                        cudaStream_t st);
+// gemm_rows > 0: qa is a materialised im2col matrix [N*P*Q][gemm_rows bytes] and wq is [K][gemm_rows]; the main loop
+// then runs as a 1x1 convolution over it while the epilogue keeps the real geometry g.
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st);
+                     cudaStream_t st, int gemm_rows = 0);
+int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
+                               cudaStream_t st);
 bool umma_supported(const ConvGeom& g);
 
 }  // namespace qb200

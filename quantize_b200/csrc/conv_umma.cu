@@ -30,13 +30,15 @@ constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each ow
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
 constexpr int kTailBytes = 256 + 2 * kConstFloats * 4;  // barriers + two constant buffers
+constexpr int kMaxWpreBytes = 2 * 16 * 1024;             // staged border tables (two buffers) for layers with R*S > 1
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
 constexpr int kMaxStages = 8;
 constexpr size_t kSmemBudget = 200 * 1024;
 
 struct UmmaParams {
-    ConvGeom g;
+    ConvGeom g;        // the convolution (epilogue: output addressing, border windows)
+    ConvGeom gm;       // what the main loop iterates: g itself, or a 1x1 "conv" over materialised im2col rows
     EpilogueParams ep;
     int KC;            // channel bytes per k-block: 32, 64 or 128 (== swizzle span)
     int BN;            // out-channel tile: 64, 128 or 256
@@ -47,6 +49,7 @@ struct UmmaParams {
     uint32_t idesc;
     uint32_t sbo16;    // stride-byte-offset >> 4 (8 rows * KC bytes)
     uint32_t layout;   // UMMA smem layout type
+    int wpre_smem;     // bytes of one staged border-table buffer (0: read the tables from global memory)
     int* err_flag;     // device int: set non-zero by the watchdog
 };
 
@@ -173,6 +176,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
 
     const ConvGeom& g = prm.g;
+    const ConvGeom& gm = prm.gm;
     const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
     const uint32_t a_bytes = kBM * KC, b_bytes = BN * KC, stage_bytes = a_bytes + b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
@@ -182,11 +186,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][3][256]
+    int32_t* wpre_s = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][BN][(R+1)(S+1)]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = prm.m_tiles * prm.n_tiles;
-    const int kblocks = g.R * g.S * prm.cblocks;
+    const int kblocks = gm.R * gm.S * prm.cblocks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -212,24 +217,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            const int PQ = g.P * g.Q;
+            const int PQ = gm.P * gm.Q;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % prm.n_tiles;
                 const int m_tile = tile / prm.n_tiles;
                 const int64_t m0 = (int64_t)m_tile * kBM;
                 const int img = (int)(m0 / PQ);
                 const int rem = (int)(m0 - (int64_t)img * PQ);
-                const int p0 = rem / g.Q, q0 = rem - p0 * g.Q;
-                const int cw = q0 * g.stride - g.pad, ch = p0 * g.stride - g.pad;
-                for (int r = 0; r < g.R; ++r)
-                    for (int s = 0; s < g.S; ++s)
+                const int p0 = rem / gm.Q, q0 = rem - p0 * gm.Q;
+                const int cw = q0 * gm.stride - gm.pad, ch = p0 * gm.stride - gm.pad;
+                for (int r = 0; r < gm.R; ++r)
+                    for (int s = 0; s < gm.S; ++s)
                         for (int cb = 0; cb < prm.cblocks; ++cb) {
                             mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
                             mbar_expect_tx(&full[stage], stage_bytes);
                             tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
-                            tma_load_2d(sb, &tmap_b, &full[stage], (r * g.S + s) * g.Cp + cb * KC, n_tile * BN);
+                            tma_load_2d(sb, &tmap_b, &full[stage], (r * gm.S + s) * gm.Cp + cb * KC, n_tile * BN);
                             if (++stage == stages) { stage = 0; phase ^= 1; }
                         }
             }
@@ -284,7 +289,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float* sc = consts + (prm.n_tiles > 1 ? buf : 0) * kConstFloats;
             float* be = sc + 256;
             float* br = sc + 512;
+            const int tbl = (g.R + 1) * (g.S + 1);
+            const int32_t* wtab = ep.wpre + (int64_t)k_base * tbl;  // border tables of this tile's channels
+            int kmax_tab = g.K - k_base;                            // rows of wtab that exist
             if (iter == 0 || prm.n_tiles > 1) {
+                if (prm.wpre_smem > 0 && es.z_a != 0.f) {
+                    int32_t* dst = wpre_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wpre_smem / 4);
+                    const int n_ent = min(BN, kmax_tab) * tbl;
+                    for (int i = et; i < n_ent; i += kEpiWarps * 32) dst[i] = __ldg(wtab + i);
+                }
                 if (et < BN) {
                     const int k = k_base + et;
                     float scale = 0.f, bias = 0.f, beff = 0.f;
@@ -310,7 +323,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int p = pq / g.Q, q = pq - p * g.Q;
             const PixelWindow pw = pixel_window(g, p, q);
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
+            // a warp with any border pixel computes the window form for all its lanes (no double execution)
+            const bool warp_interior = __all_sync(0xffffffffu, interior || !row_ok);
             const bool full_n = k_base + BN <= g.K;
+            const int32_t* wt = (prm.wpre_smem > 0 && es.z_a != 0.f)
+                                    ? wpre_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wpre_smem / 4) : wtab;
+            const int s1 = g.S + 1;
+            const int i11 = pw.r1 * s1 + pw.s1, i01 = pw.r0 * s1 + pw.s1, i10 = pw.r1 * s1 + pw.s0, i00 = pw.r0 * s1 + pw.s0;
             const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
 
             mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
@@ -322,7 +341,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 tmem_ld_wait();
                 const int cc = half * cols + c0;  // first column of this chunk inside the tile
                 if (!row_ok) continue;
-                if (!acc_out && full_n && interior) {
+                if (!acc_out && full_n && warp_interior) {
                     float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -347,10 +366,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         const int k = k_base + cc + j;
                         if (k >= g.K) continue;
                         float r;
-                        if (interior) {
+                        if (es.z_a == 0.f) {
                             r = __fmaf_rn((float)(int32_t)v[j], sc[cc + j], be[cc + j]);
                         } else {
-                            const float t = __fmaf_rn(es.z_a, (float)window_wsum(ep.wpre, k, g.R, g.S, pw), (float)(int32_t)v[j]);
+                            const int32_t* t4 = wt + (cc + j) * tbl;
+                            const int32_t ws = t4[i11] - t4[i01] - t4[i10] + t4[i00];
+                            const float t = __fmaf_rn(es.z_a, (float)ws, (float)(int32_t)v[j]);
                             r = __fmaf_rn(sc[cc + j], t, br[cc + j]);
                         }
                         o[(int64_t)j * PQ] = r;
@@ -444,8 +465,17 @@ bool umma_supported(const ConvGeom& g) {
 }
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st) {
+                     cudaStream_t st, int gemm_rows) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
+    ConvGeom gm = g;
+    if (gemm_rows > 0) {  // materialised im2col rows: a 1x1 convolution over an [N, P, Q, gemm_rows] tensor
+        gm.C = gm.Cg = gm.Cp = gm.Cgp = gemm_rows;
+        gm.H = g.P;
+        gm.W = g.Q;
+        gm.R = gm.S = 1;
+        gm.stride = 1;
+        gm.pad = 0;
+    }
     const DriverApi& api = driver_api();
     QB_REQUIRE(api.ok, QB200_EDRIVER, "cuTensorMapEncodeTiled/Im2col driver entry points unavailable");
     QB_REQUIRE(reinterpret_cast<uintptr_t>(qa) % 16 == 0 && reinterpret_cast<uintptr_t>(wq) % 16 == 0, QB200_EINVAL,
@@ -453,11 +483,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
 
     UmmaParams prm;
     prm.g = g;
+    prm.gm = gm;
     prm.ep = ep;
     prm.M = (int64_t)g.N * g.P * g.Q;
     if (prm.M == 0) return 0;
-    prm.KC = (g.Cp % 128 == 0) ? 128 : (g.Cp % 64 == 0) ? 64 : 32;
-    prm.cblocks = g.Cp / prm.KC;
+    prm.KC = (gm.Cp % 128 == 0) ? 128 : (gm.Cp % 64 == 0) ? 64 : 32;
+    prm.cblocks = gm.Cp / prm.KC;
     prm.m_tiles = (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
@@ -466,7 +497,10 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.BN = BN;
     prm.n_tiles = (g.K + BN - 1) / BN;
     const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
-    int stages = (int)((kSmemBudget - 1024 - kTailBytes) / stage_bytes);
+    const int tbl_bytes = BN * (g.R + 1) * (g.S + 1) * 4;
+    prm.wpre_smem = (g.R * g.S > 1 && 2 * tbl_bytes <= kMaxWpreBytes) ? tbl_bytes : 0;
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wpre_smem;
+    int stages = (int)((kSmemBudget - 1024 - tail) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
     prm.stages = stages;
@@ -482,24 +516,24 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     alignas(64) CUtensorMap tmap_a, tmap_b;
     {
         // activations: (C, W, H, N) u8, im2col mode; base pixel of an output (p,q) is (q*stride - pad, p*stride - pad)
-        cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
-        cuuint64_t strides[3] = {(cuuint64_t)g.Cp, (cuuint64_t)g.W * g.Cp, (cuuint64_t)g.H * g.W * g.Cp};
-        int lower[2] = {-g.pad, -g.pad};
-        int upper[2] = {g.pad - (g.S - 1), g.pad - (g.R - 1)};
-        cuuint32_t estr[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+        cuuint64_t dims[4] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W, (cuuint64_t)gm.H, (cuuint64_t)gm.N};
+        cuuint64_t strides[3] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W * gm.Cp, (cuuint64_t)gm.H * gm.W * gm.Cp};
+        int lower[2] = {-gm.pad, -gm.pad};
+        int upper[2] = {gm.pad - (gm.S - 1), gm.pad - (gm.R - 1)};
+        cuuint32_t estr[4] = {1, (cuuint32_t)gm.stride, (cuuint32_t)gm.stride, 1};
         CUresult r = api.im2col(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<uint8_t*>(qa), dims, strides, lower,
                                 upper, (cuuint32_t)prm.KC, (cuuint32_t)kBM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
         // driver <= 13.1 encodes im2col maps of tensors below 128 KiB with a bit that makes the unit fault;
         // the same adjustment NVIDIA's own CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp)
-        if (api.driver_version <= 13010 && (size_t)g.N * g.H * g.W * g.Cp < 131072)
+        if (api.driver_version <= 13010 && (size_t)gm.N * gm.H * gm.W * gm.Cp < 131072)
             reinterpret_cast<uint64_t*>(&tmap_a)[1] &= ~(1ull << 21);
     }
     {
         // weights: [K rows][R*S*Cp bytes], tiled mode, rows beyond K zero-filled
-        cuuint64_t dims[2] = {(cuuint64_t)g.R * g.S * g.Cp, (cuuint64_t)g.K};
-        cuuint64_t strides[1] = {(cuuint64_t)g.R * g.S * g.Cp};
+        cuuint64_t dims[2] = {(cuuint64_t)gm.R * gm.S * gm.Cp, (cuuint64_t)g.K};
+        cuuint64_t strides[1] = {(cuuint64_t)gm.R * gm.S * gm.Cp};
         cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)BN};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = api.tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(wq), dims, strides, box, estr,
@@ -508,7 +542,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + kTailBytes;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + tail;
     static thread_local size_t smem_set = 0;
     if (smem > smem_set) {
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));

@@ -19,6 +19,12 @@ PreparedLayout prepared_layout(const qb200_conv_shape& s) {
     L.wq_bytes = align_up_sz((size_t)s.K * s.R * s.S * L.Cgp, 256);
     L.wpre_off = L.wq_bytes;
     L.total = L.wpre_off + align_up_sz((size_t)s.K * (s.R + 1) * (s.S + 1) * sizeof(int32_t), 256);
+    L.Kcol = 0;
+    L.wcol_off = L.total;
+    if (uses_im2col_rows(s)) {
+        L.Kcol = im2col_row_bytes(s.R, s.S);
+        L.total = L.wcol_off + align_up_sz((size_t)s.K * L.Kcol, 256);
+    }
     return L;
 }
 
@@ -59,6 +65,18 @@ __global__ void unpack_weights_kernel(const uint8_t* __restrict__ packed, uint8_
         v = (uint8_t)(((w >> off) & ((1u << nb) - 1u)) - offset);  // :97-102
     }
     wq[i] = v;
+}
+
+// im2col weight rows: byte (r*S + s)*4 + c of row k = wq[k][r][s][c], zero elsewhere
+__global__ void im2col_weights_kernel(const uint8_t* __restrict__ wq, uint8_t* __restrict__ wcol, int K, int C, int R, int S,
+                                      int Cgp, int Kcol) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)K * Kcol) return;
+    const int k = (int)(i / Kcol), b = (int)(i % Kcol);
+    const int tap = b >> 2, c = b & 3;
+    uint8_t v = 0;
+    if (tap < R * S && c < C) v = wq[((int64_t)k * R * S + tap) * Cgp + c];
+    wcol[i] = v;
 }
 
 // one warp per output channel
@@ -109,7 +127,13 @@ size_t qb200_conv_prepared_bytes(const qb200_conv_shape* s) {
 size_t qb200_conv_workspace_bytes(const qb200_conv_shape* s) {
     using namespace qb200;
     if (validate_shape(s)) return 0;
-    return align_up_sz((size_t)s->N * s->H * s->W * qb200_padded_channels(s->C), 256);
+    size_t bytes = (size_t)s->N * s->H * s->W * qb200_padded_channels(s->C);
+    if (uses_im2col_rows(*s)) {
+        const size_t P = (s->H + 2 * s->pad - s->R) / s->stride + 1, Q = (s->W + 2 * s->pad - s->S) / s->stride + 1;
+        const size_t col = (size_t)s->N * P * Q * im2col_row_bytes(s->R, s->S);
+        if (col > bytes) bytes = col;
+    }
+    return align_up_sz(bytes, 256);
 }
 
 int qb200_conv_prepare_weights(const qb200_conv_shape* s, const uint8_t* w_packed, void* prepared, void* stream) {
@@ -129,6 +153,11 @@ int qb200_conv_prepare_weights(const qb200_conv_shape* s, const uint8_t* w_packe
     QB_LAUNCH_CHECK();
     tap_prefix_kernel<<<s->K, 32, 0, st>>>(wq, wpre, s->K, s->R, s->S, L.Cgp, s->w_sign ? 1 : 0);
     QB_LAUNCH_CHECK();
+    if (L.Kcol) {
+        im2col_weights_kernel<<<(unsigned)ceil_div64((int64_t)s->K * L.Kcol, 256), 256, 0, st>>>(
+            wq, wq + L.wcol_off, s->K, s->C, s->R, s->S, L.Cgp, L.Kcol);
+        QB_LAUNCH_CHECK();
+    }
     return 0;
 }
 
