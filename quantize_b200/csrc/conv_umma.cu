@@ -12,8 +12,8 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
 // warps 2..9 = epilogue (tcgen05.ld -> dequant -> coalesced NCHW stores: a TMEM lane is an output pixel, so the 32
 // lanes of a warp write 32 consecutive pixels of one output channel = one 128-byte line).  The per-channel
-// constants (s_a*s_w[k], bias[k] + s_a*s_w[k]*z_a*sum(qw[k])) are staged in shared memory once per tile so that an
-// interior pixel costs one convert + one FMA + one store per output element; border pixels of a layer with a
+// constants (s_a*s_w[k], bias[k], sum(qw[k])) are staged in shared memory once per tile so that an
+// interior pixel costs one convert + one or two FMAs + one store per output element (every path rounds identically); border pixels of a layer with a
 // non-zero activation zero point take the 4-corner prefix-sum path.
 // Persistent: grid = #SMs, static round-robin tile schedule, output-channel tiles fastest so concurrently
 // running CTAs share the same activation slice in L2.
@@ -300,15 +300,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 if (et < BN) {
                     const int k = k_base + et;
-                    float scale = 0.f, bias = 0.f, beff = 0.f;
+                    float scale = 0.f, bias = 0.f, beff = 0.f;  // beff: sum of all taps' weights (interior window), as float
                     if (k < g.K) {
                         scale = __fmul_rn(es.s_a, __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k)));
                         bias = ep.bias ? __ldg(ep.bias + k) : 0.f;
-                        beff = bias;
-                        if (es.z_a != 0.f) {
-                            const int32_t wfull = __ldg(ep.wpre + (int64_t)(k + 1) * (g.R + 1) * (g.S + 1) - 1);
-                            beff = __fmaf_rn(scale, __fmul_rn(es.z_a, (float)wfull), bias);
-                        }
+                        if (es.z_a != 0.f) beff = (float)__ldg(ep.wpre + (int64_t)(k + 1) * (g.R + 1) * (g.S + 1) - 1);
                     }
                     sc[et] = scale;
                     be[et] = beff;
@@ -343,15 +339,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (!row_ok) continue;
                 if (!acc_out && full_n && warp_interior) {
                     float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
+                    // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias)
+                    if (es.z_a == 0.f) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                        const float4 b4 = *reinterpret_cast<const float4*>(be + cc + j);
-                        o[0] = __fmaf_rn((float)(int32_t)v[j + 0], s4.x, b4.x);
-                        o[PQ] = __fmaf_rn((float)(int32_t)v[j + 1], s4.y, b4.y);
-                        o[2 * (int64_t)PQ] = __fmaf_rn((float)(int32_t)v[j + 2], s4.z, b4.z);
-                        o[3 * (int64_t)PQ] = __fmaf_rn((float)(int32_t)v[j + 3], s4.w, b4.w);
-                        o += 4 * (int64_t)PQ;
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+                            const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
+                            o[0] = __fmaf_rn(s4.x, (float)(int32_t)v[j + 0], b4.x);
+                            o[PQ] = __fmaf_rn(s4.y, (float)(int32_t)v[j + 1], b4.y);
+                            o[2 * (int64_t)PQ] = __fmaf_rn(s4.z, (float)(int32_t)v[j + 2], b4.z);
+                            o[3 * (int64_t)PQ] = __fmaf_rn(s4.w, (float)(int32_t)v[j + 3], b4.w);
+                            o += 4 * (int64_t)PQ;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+                            const float4 w4 = *reinterpret_cast<const float4*>(be + cc + j);
+                            const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
+                            o[0] = __fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x);
+                            o[PQ] = __fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y);
+                            o[2 * (int64_t)PQ] = __fmaf_rn(s4.z, __fmaf_rn(es.z_a, w4.z, (float)(int32_t)v[j + 2]), b4.z);
+                            o[3 * (int64_t)PQ] = __fmaf_rn(s4.w, __fmaf_rn(es.z_a, w4.w, (float)(int32_t)v[j + 3]), b4.w);
+                            o += 4 * (int64_t)PQ;
+                        }
                     }
                 } else if (acc_out) {
                     int32_t* o = static_cast<int32_t*>(out) + o_base + (int64_t)cc * PQ;
@@ -367,7 +378,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (k >= g.K) continue;
                         float r;
                         if (es.z_a == 0.f) {
-                            r = __fmaf_rn((float)(int32_t)v[j], sc[cc + j], be[cc + j]);
+                            r = __fmaf_rn(sc[cc + j], (float)(int32_t)v[j], br[cc + j]);
                         } else {
                             const int32_t* t4 = wt + (cc + j) * tbl;
                             const int32_t ws = t4[i11] - t4[i01] - t4[i10] + t4[i00];
