@@ -184,30 +184,53 @@ class ConvStack:
             max_ws = max(max_ws, self.L.qb200_conv_workspace_bytes(ctypes.byref(shape)))
             max_out = max(max_out, s["N"] * s["K"] * P * Q)
             ops = 2 * s["N"] * s["K"] * P * Q * cg * s["R"] * s["R"]
-            conv_bytes = s["N"] * s["H"] * s["W"] * Cp + s["K"] * s["R"] * s["R"] * Cp + 4 * s["N"] * s["K"] * P * Q + 12 * s["K"]
-            quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * s["H"] * s["W"] * Cp
+            single = bool(self.L.qb200_conv_is_single_kernel(ctypes.byref(shape), x.data_ptr()))
+            w_bytes = s["K"] * s["R"] * s["R"] * Cp + 12 * s["K"]
+            if single:   # one kernel: fp32 in, fp32 out
+                conv_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + w_bytes + 4 * s["N"] * s["K"] * P * Q
+                quant_bytes = 0
+            else:        # quantizer kernel (fp32 in, u8 out) + conv kernel (u8 in, fp32 out)
+                conv_bytes = s["N"] * s["H"] * s["W"] * Cp + w_bytes + 4 * s["N"] * s["K"] * P * Q
+                quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * s["H"] * s["W"] * Cp
             self.layers.append(dict(spec=s, x=x, shape=shape, prepared=prepared, aq=aq, aq_t=aq_t, w_scale=w_scale,
-                                    bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed))
+                                    bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed, single=single))
         self.ws = torch.empty(max_ws, dtype=torch.uint8, device=device)
         self.out = torch.empty(max_out, dtype=torch.float32, device=device)
         torch.cuda.synchronize()
 
     def step(self, stream, events=None):
-        """one pass of the hot path; events: optional list of (start, end) CUDA events around each conv launch"""
+        """one pass of the hot path; events: optional per-layer (conv start, conv end, layer start) CUDA events.
+        1x1/stride-1 layers run as ONE kernel (quantizer fused into the conv's producer warps): for them the whole call
+        is the conv kernel; the other layers run the quantizer kernel and the conv kernel."""
         L, capi = self.L, self.capi
         for i, l in enumerate(self.layers):
             s = l["spec"]
             if events is not None:
                 events[i][2].record()
-            capi.check(L.qb200_conv_quantize_input(ctypes.byref(l["shape"]), l["x"].data_ptr(), ctypes.byref(l["aq"]),
-                                                   self.ws.data_ptr(), stream), "quantize_input")
-            if events is not None:
-                events[i][0].record()
-            capi.check(L.qb200_conv_from_workspace(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
-                                                   l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
-                                                   ctypes.byref(l["aq"]), self.out.data_ptr(), capi.OUT_F32, stream), "conv")
+            if l["single"]:
+                if events is not None:
+                    events[i][0].record()
+                capi.check(L.qb200_quantconv2d_fused(ctypes.byref(l["shape"]), l["x"].data_ptr(), l["prepared"].data_ptr(),
+                                                     l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
+                                                     ctypes.byref(l["aq"]), self.ws.data_ptr(), self.out.data_ptr(),
+                                                     capi.OUT_F32, stream), "quantconv2d_fused")
+            else:
+                capi.check(L.qb200_conv_quantize_input(ctypes.byref(l["shape"]), l["x"].data_ptr(), ctypes.byref(l["aq"]),
+                                                       self.ws.data_ptr(), stream), "quantize_input")
+                if events is not None:
+                    events[i][0].record()
+                capi.check(L.qb200_conv_from_workspace(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
+                                                       l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
+                                                       ctypes.byref(l["aq"]), self.out.data_ptr(), capi.OUT_F32, stream), "conv")
             if events is not None:
                 events[i][1].record()
+            if os.environ.get("QB200_BENCH_SYNC"):      # debugging aid: localise a failing launch
+                try:
+                    self.torch.cuda.synchronize()
+                except Exception:
+                    print(f"launch failure in layer {i}: {s} single={l['single']} watchdog={L.qb200_watchdog_code()}",
+                          file=sys.stderr, flush=True)
+                    raise
 
 
 def run_b200(args):
@@ -291,7 +314,8 @@ def run_b200(args):
                 "launches_per_step": nl,
                 "conv_share_of_step": round(conv_total_ms / ms_per_step, 4),
                 "act_quantize_share_of_step": round(sum(quant_ms) / ms_per_step, 4),
-                "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (sum(quant_ms) * 1e-3) / 1e9, 1),
+                "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (max(sum(q for q, l in zip(quant_ms, stack.layers) if not l["single"]), 1e-9) * 1e-3) / 1e9, 1),
+                "single_kernel_layers": sum(1 for l in stack.layers if l["single"]),
                 "tensor_tops": round(total_ops / (conv_total_ms * 1e-3) / 1e12, 1),
                 "tensor_frac_of_int8_spec": round(total_ops / (conv_total_ms * 1e-3) / 1e12 / INT8_PEAK_TOPS, 4),
                 "step_contract_gbs": round(contract_bytes / (ms_per_step * 1e-3) / 1e9, 1),
@@ -299,8 +323,8 @@ def run_b200(args):
     if args.per_layer and rank == 0:
         for i, l in enumerate(stack.layers):
             s = l["spec"]
-            print(f"layer {i:2d} C{s['C']:4d} H{s['H']:3d} K{s['K']:4d} R{s['R']} s{s['stride']} quant {quant_ms[i]*1e3:7.1f} us "
-                  f"{l['quant_bytes']/quant_ms[i]/1e6:6.0f} GB/s | conv {conv_ms[i]*1e3:7.1f} us "
+            print(f"layer {i:2d} C{s['C']:4d} H{s['H']:3d} K{s['K']:4d} R{s['R']} s{s['stride']} {'1k' if l['single'] else '2k'} "
+                  f"quant {quant_ms[i]*1e3:7.1f} us {l['quant_bytes']/max(quant_ms[i],1e-9)/1e6:6.0f} GB/s | conv {conv_ms[i]*1e3:7.1f} us "
                   f"{l['conv_bytes']/conv_ms[i]/1e6:6.0f} GB/s {l['ops']/conv_ms[i]/1e9:6.0f} TOPS", file=sys.stderr)
 
     # ---- end to end through the public op API: host images -> logits on host ----------------------------
@@ -314,22 +338,37 @@ def run_b200(args):
         hw = models.INPUT_HW[args.model]
         host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
         host_out = torch.empty(args.batch, 1000, dtype=torch.float32).pin_memory()
-        dev_in = torch.empty_like(host_in, device=device)
+        dev_in = [torch.empty_like(host_in, device=device) for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=device)
+        compute = torch.cuda.current_stream()
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
-            dev_in.copy_(host_in, non_blocking=True)
-            with torch.no_grad():
-                logits = net(dev_in)
-            host_out.copy_(logits, non_blocking=True)
+        def issue_copy(k):          # H2D of step k's images on the copy stream, into the buffer step k-2 has released
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_used[k % 2])
+                dev_in[k % 2].copy_(host_in, non_blocking=True)
+                ev_copied[k % 2].record(copy_stream)
 
-        for _ in range(max(args.warmup, 1)):
-            e2e_step()
+        def e2e_steps(n):           # every step: H2D of its inputs, forward, D2H of its logits; copies overlap compute
+            issue_copy(0)
+            for k in range(n):
+                if k + 1 < n:
+                    issue_copy(k + 1)
+                compute.wait_event(ev_copied[k % 2])
+                with torch.no_grad():
+                    logits = net(dev_in[k % 2])
+                ev_used[k % 2].record(compute)
+                host_out.copy_(logits, non_blocking=True)
+
+        for ev in ev_used:
+            ev.record(compute)
+        e2e_steps(max(args.warmup, 1))
         barrier()
         L.qb200_launch_count_reset()
         wall0 = time.perf_counter()
         t0.record()
-        for _ in range(K):
-            e2e_step()
+        e2e_steps(K)
         t1.record()
         barrier()
         wall = time.perf_counter() - wall0
@@ -342,6 +381,7 @@ def run_b200(args):
                "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                "ms_per_step": round(e_ms / K, 3), "wall_ms_per_step": round(wall / K * 1e3, 3),
                "api": "models.build_packed(resnet50) forward: host.QuantConv2d -> quant_engine.quantconv2d_float_input",
+               "pipelining": "H2D of step k+1 (copy stream, double buffer) overlaps the forward of step k; all copies inside the timed region",
                "engine_launches_per_step": int(L.qb200_launch_count()) // K}
 
     cpu_baseline = None
@@ -369,7 +409,25 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def _only_json_on_stdout():
+    """NCCL / torch may print to fd 1 (e.g. 'NCCL version ...'); the contract is ONE JSON line on stdout.  Everything
+    else is sent to stderr, and the JSON line is written to the real stdout at the end."""
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    _print = print
+
+    def json_print(*a, **k):
+        if k.get("file") is None and a and isinstance(a[0], str) and a[0].startswith("{"):
+            out.write(a[0] + "\n")
+            out.flush()
+        else:
+            _print(*a, **k)
+    return json_print
+
+
 if __name__ == "__main__":
+    print = _only_json_on_stdout()   # noqa: A001
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

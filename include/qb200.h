@@ -131,6 +131,12 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
 #define QB200_ALGO_AUTO 0   /* tcgen05 implicit GEMM when groups == 1, CUDA-core kernel otherwise       */
 #define QB200_ALGO_DIRECT 1 /* CUDA-core direct conv (any groups)                                      */
 #define QB200_ALGO_UMMA 2   /* TMA im2col + tcgen05.mma kind::i8 + TMEM accumulators (groups == 1)      */
+#define QB200_ALGO_UMMA_TWO_KERNELS 3 /* as 2, but never fuse the quantizer into the conv kernel (A/B tests) */
+#define QB200_ALGO_UMMA_FUSED_QUANT 4 /* as 2, and fuse the quantizer wherever it is supported (tests)       */
+/* Every mbarrier wait of the tensor-core kernel is bounded (~4 s): on expiry the kernel records which wait it was
+ * (1 TMA producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue, 5-7 fused-quantize producers) and traps instead of
+ * hanging the GPU.  0 = never fired.  Readable after the trap (mapped host memory). */
+int qb200_watchdog_code(void);
 void qb200_set_conv_algo(int algo);
 int qb200_get_conv_algo(void);
 
@@ -145,6 +151,11 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
                             const float* w_scale, int32_t n_w_scale, const float* bias,
                             const qb200_act_quant* aq, void* workspace, void* out, int32_t out_kind,
                             void* stream);
+
+/* 1 when qb200_quantconv2d_fused runs this layer as ONE kernel (the quantizer runs in the conv kernel's producer warps
+ * and no workspace is written), else 0.  Supported for 1x1, stride 1, pad 0, C % 64 == 0, H*W % 4 == 0, 16-byte
+ * aligned x; chosen by default where it was measured to win (C == 64, feature map >= 28x28). */
+int qb200_conv_is_single_kernel(const qb200_conv_shape* s, const float* x);
 
 /* The two kernels of the fused op as separate calls (same result as qb200_quantconv2d_fused; lets a caller time or
  * overlap them).  The workspace layout is private to the pair: NHWC(Cp) bytes, or — for layers with <= 4 input

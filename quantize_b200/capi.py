@@ -16,12 +16,12 @@ SYMBOLS = [
     "qb200_conv_out_hw", "qb200_padded_channels", "qb200_conv_prepared_bytes", "qb200_conv_prepare_weights",
     "qb200_conv_workspace_bytes", "qb200_act_quantize_nhwc", "qb200_set_conv_algo", "qb200_get_conv_algo",
     "qb200_quantconv2d_fused", "qb200_conv2d_q8_nhwc", "qb200_quantconv2d_weightonly",
-    "qb200_conv_quantize_input", "qb200_conv_from_workspace",
+    "qb200_conv_quantize_input", "qb200_conv_from_workspace", "qb200_conv_is_single_kernel", "qb200_watchdog_code",
 ]
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
 OUT_F32, OUT_ACC = 0, 1
-ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA = 0, 1, 2
+ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA, ALGO_UMMA_TWO_KERNELS, ALGO_UMMA_FUSED_QUANT = 0, 1, 2, 3, 4
 
 
 class ConvShape(ctypes.Structure):
@@ -71,6 +71,7 @@ def lib():
         L.qb200_get_conv_algo.restype = ctypes.c_int
         L.qb200_quantconv2d_fused.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, vp, i32, vp]
         L.qb200_conv2d_q8_nhwc.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, i32, vp]
+        L.qb200_conv_is_single_kernel.argtypes = [sp, vp]
         L.qb200_conv_quantize_input.argtypes = [sp, vp, ap, vp, vp]
         L.qb200_conv_from_workspace.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, i32, vp]
         L.qb200_quantconv2d_weightonly.argtypes = [sp, vp, vp, vp, vp, i32, vp, vp, vp]

@@ -6,10 +6,10 @@
 // and changes the layout to channel-last so that the implicit-GEMM conv can fetch K-contiguous im2col
 // rows with TMA.  Channels C..Cp-1 are written as 0 (they meet zero weights in the MMA).
 //
-// Bit-exactness without paying an IEEE division per element: t' = fma(x, 1/scale, -zero) differs from the
-// reference's fl(fl(x/scale) - zero) by at most (|t| + |zero| + 1) * 2^-22, so rint(t') == rint(t) unless t' lies
-// within that margin of a rounding boundary (k + 0.5); only those elements (about 1 in 10^4) — and NaN / huge
-// values — take the exact divide.  tests/test_conv_gpu.py checks the integers against the oracle bit for bit.
+// Bit-exactness without an IEEE division per element and without data-dependent branches: quant_math.cuh computes
+// RN(x/s) as x*RN(1/s) followed by two exact-residual FMA corrections (Markstein), then RN(. - z) and a magic-number
+// round-to-nearest-even; tests/test_conv_gpu.py checks the integers against the oracle bit for bit, including inputs
+// placed on and one ulp around every rounding boundary.
 //
 // Machine mapping (vector kernel, H*W % 4 == 0): a block is 128 consecutive pixels; a thread owns 4 consecutive
 // pixels x 16 channels: 16 coalesced 16-byte loads (a warp reads 512 contiguous bytes of one channel plane),
@@ -17,6 +17,7 @@
 // copies the tile out as whole contiguous NHWC rows.  HBM-bound: bytes per element = 4 (read) + Cp/C (write).
 #include "common.cuh"
 #include "conv_common.cuh"
+#include "quant_math.cuh"
 
 namespace qb200 {
 namespace {
@@ -24,76 +25,6 @@ namespace {
 constexpr int kPix = 128;  // pixels per block
 constexpr int kThreads = 128;
 constexpr int kCw = 128;   // channel bytes per shared-memory pass
-
-struct QuantParams {
-    float s, z, lo, hi;  // the reference's parameters
-    float r, nz, thr;    // 1/s, -z, fast-path threshold on |t' - rint(t')|
-    uint32_t lo4, hi4;   // qmin / qmax replicated into 4 bytes (valid when fast_clamp)
-    int fast_clamp;      // 0 <= qmin <= qmax <= 255 and both integral
-};
-
-__device__ __forceinline__ QuantParams load_params(const float* p_scale, const float* p_zero, const float* p_qmin,
-                                                   const float* p_qmax) {
-    QuantParams p;
-    p.s = __ldg(p_scale);
-    p.z = __ldg(p_zero);
-    p.lo = __ldg(p_qmin);
-    p.hi = __ldg(p_qmax);
-    p.r = __frcp_rn(p.s);
-    p.nz = -p.z;
-    const float maxq = fmaxf(fabsf(p.lo), fabsf(p.hi)) + 1.f;
-    p.thr = 0.5f - (maxq + fabsf(p.z) + 1.f) * 4.76837158203125e-7f;  // 2^-21
-    p.fast_clamp = (p.lo >= 0.f && p.hi <= 255.f && p.lo <= p.hi && p.lo == rintf(p.lo) && p.hi == rintf(p.hi)) ? 1 : 0;
-    const uint32_t l = (uint32_t)(int)fminf(fmaxf(p.lo, 0.f), 255.f), h = (uint32_t)(int)fminf(fmaxf(p.hi, 0.f), 255.f);
-    p.lo4 = l * 0x01010101u;
-    p.hi4 = h * 0x01010101u;
-    if (!p.fast_clamp) p.thr = -1.f;  // quantizers outside [0, 255]: every word takes the exact path
-    return p;
-}
-
-// the reference's arithmetic, verbatim, for the four channels of one output word (results clamped)
-__device__ __noinline__ uint32_t quant_word_exact(float x0, float x1, float x2, float x3, float s, float z, float lo, float hi) {
-    const float xs[4] = {x0, x1, x2, x3};
-    uint32_t w = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float t = __fsub_rn(__fdiv_rn(xs[i], s), z);  // x / scale - zero, no contraction
-        t = rintf(t);                                 // torch.round: half to even
-        t = fminf(fmaxf(t, lo), hi);                  // clamp(qmin, qmax); a NaN activation maps to qmin
-        w |= ((uint32_t)(int)t & 0xFFu) << (8 * i);
-    }
-    return w;
-}
-
-// One output word = four channels of one pixel.  Fast path: t' = fma(x, 1/s, -z); adding 1.5*2^23 rounds it to the
-// nearest-even integer in the low mantissa bits; it is trusted when t' is farther than the error bound from a
-// rounding boundary and small enough for the trick; saturating pack + byte-wise min/max do the clamp.  If any of
-// the four needs it (about 1 word in 10^3), the whole word is recomputed with the reference's exact arithmetic.
-__device__ __forceinline__ uint32_t quant_word(float x0, float x1, float x2, float x3, const QuantParams& p) {
-    const float magic = 12582912.f;
-    const float xs[4] = {x0, x1, x2, x3};
-    int q[4];
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float t = __fmaf_rn(xs[i], p.r, p.nz);
-        const float u = __fadd_rn(t, magic);
-        const float d = fabsf(__fsub_rn(t, __fsub_rn(u, magic)));
-        q[i] = __float_as_int(u) - 0x4B400000;
-        ok = ok && (d < p.thr) && (fabsf(t) < 2097152.f);
-    }
-    if (!ok) return quant_word_exact(x0, x1, x2, x3, p.s, p.z, p.lo, p.hi);
-    uint32_t hi16, w;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(q[3]), "r"(q[2]), "r"(0));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(q[1]), "r"(q[0]), "r"(hi16));
-    return __vminu4(__vmaxu4(w, p.lo4), p.hi4);
-}
-
-__device__ __forceinline__ float4 ldg_stream4(const float* p) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
 
 __device__ __forceinline__ void copy_out(const uint4* tile, uint8_t* __restrict__ q, int64_t g0, int n_rows, int chunks, int Cp,
                                          int c_base) {

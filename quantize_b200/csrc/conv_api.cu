@@ -10,7 +10,15 @@ int g_conv_algo = QB200_ALGO_AUTO;
 int resolve_algo(const ConvGeom& g) {
     int algo = g_conv_algo;
     if (algo == QB200_ALGO_AUTO) algo = umma_supported(g) ? QB200_ALGO_UMMA : QB200_ALGO_DIRECT;
+    if (algo == QB200_ALGO_UMMA_TWO_KERNELS || algo == QB200_ALGO_UMMA_FUSED_QUANT) algo = QB200_ALGO_UMMA;
     return algo;
+}
+
+// 1x1 / stride-1 layers: the quantizer runs inside the tensor-core kernel's producer warps (one kernel, no workspace)
+bool single_kernel(const ConvGeom& g, const float* x) {
+    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || resolve_algo(g) != QB200_ALGO_UMMA) return false;
+    if (!umma_fused_quant_supported(g, x)) return false;
+    return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_fused_quant_profitable(g);
 }
 
 // does the conv kernel chosen for this shape read materialised im2col rows (few-channel layers) or NHWC(Cp) bytes?
@@ -26,11 +34,12 @@ int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_qu
 
 // from_ws: `q` is the workspace written by quantize_input (layout per workspace_is_im2col); else NHWC(Cp) bytes
 int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const void* prepared, const float* w_scale,
-             int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind, cudaStream_t st) {
+             int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind, cudaStream_t st,
+             const float* x_fused = nullptr) {
     QB_REQUIRE(n_w_scale == 1 || n_w_scale == s->K, QB200_EINVAL, "weight_scale must have 1 or K elements");
     QB_REQUIRE(out_kind == QB200_OUT_F32 || out_kind == QB200_OUT_ACC, QB200_EINVAL, "conv: bad out_kind");
     QB_REQUIRE(aq && aq->scale && aq->zero, QB200_EINVAL, "conv: activation quantizer parameters missing");
-    QB_REQUIRE(q && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
+    QB_REQUIRE((q || x_fused) && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
     const ConvGeom g = make_geom(*s);
     const PreparedLayout L = prepared_layout(*s);
     const uint8_t* wq = static_cast<const uint8_t*>(prepared);
@@ -42,6 +51,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     ep.wpre = reinterpret_cast<const int32_t*>(wq + L.wpre_off);
     ep.per_tensor_w = n_w_scale == 1;
     ep.out_kind = out_kind;
+    if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(g, q, wq, ep, out, st);
     return launch_conv_direct(g, q, wq, ep, out, st);
@@ -51,6 +61,8 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
 }  // namespace qb200
 
 extern "C" {
+
+int qb200_watchdog_code(void) { return qb200::watchdog_code(); }
 
 void qb200_set_conv_algo(int algo) { qb200::g_conv_algo = algo; }
 int qb200_get_conv_algo(void) { return qb200::g_conv_algo; }
@@ -62,6 +74,12 @@ int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const
     if (int rc = validate_shape(s)) return rc;
     if (s->N == 0) return 0;
     return run_conv(s, q_nhwc, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, static_cast<cudaStream_t>(stream));
+}
+
+int qb200_conv_is_single_kernel(const qb200_conv_shape* s, const float* x) {
+    using namespace qb200;
+    if (validate_shape(s)) return 0;
+    return single_kernel(make_geom(*s), x) ? 1 : 0;
 }
 
 int qb200_conv_quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, void* workspace,
@@ -89,7 +107,10 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
     if (int rc = validate_shape(s)) return rc;
     if (s->N == 0) return 0;
     QB_REQUIRE(workspace != nullptr, QB200_EINVAL, "conv: workspace missing (qb200_conv_workspace_bytes)");
+    QB_REQUIRE(x != nullptr, QB200_EINVAL, "conv: null input");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (single_kernel(make_geom(*s), x))
+        return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x);
     if (int rc = quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), st)) return rc;
     return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st);
 }

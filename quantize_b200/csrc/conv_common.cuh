@@ -99,10 +99,16 @@ int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, 
                        cudaStream_t st);
 // gemm_rows > 0: qa is a materialised im2col matrix [N*P*Q][gemm_rows bytes] and wq is [K][gemm_rows]; the main loop
 // then runs as a 1x1 convolution over it while the epilogue keeps the real geometry g.
+// x_fused != nullptr: 1x1 / stride-1 layer whose A operand is quantized inside the kernel from the fp32 NCHW input
+// (see umma_fused_quant_supported); qa is then ignored.
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st, int gemm_rows = 0);
+                     cudaStream_t st, int gemm_rows = 0, const float* x_fused = nullptr,
+                     const qb200_act_quant* aq_fused = nullptr);
+bool umma_fused_quant_supported(const ConvGeom& g, const float* x);
+bool umma_fused_quant_profitable(const ConvGeom& g);
 int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
                                cudaStream_t st);
 bool umma_supported(const ConvGeom& g);
+int watchdog_code();
 
 }  // namespace qb200

@@ -19,6 +19,7 @@
 // running CTAs share the same activation slice in L2.
 #include "common.cuh"
 #include "conv_common.cuh"
+#include "quant_math.cuh"
 
 #include <cuda.h>
 
@@ -28,6 +29,10 @@ namespace {
 constexpr int kBM = 128;            // pixels per tile = TMEM lanes = UMMA M
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each owns half of the tile's columns
 constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kFqWarps = 8;         // fused-quantize variant: quantizer warps, each owns 8 channels x 128 pixels of a k-block
+constexpr int kThreadsFq = kThreads + 32 + kFqWarps * 32;  // + one TMA warp for the fp32 tiles
+constexpr int kXStages = 3;         // fp32 staging ring of the fused-quantize variant
+constexpr int kFqKC = 64;           // its k-block: 64 channels (a 32 KB fp32 tile, an 8 KB u8 A tile)
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
 constexpr int kTailBytes = 256 + 2 * kConstFloats * 4;  // barriers + two constant buffers
 constexpr int kMaxWpreBytes = 2 * 16 * 1024;             // staged border tables (two buffers) for layers with R*S > 1
@@ -51,6 +56,13 @@ struct UmmaParams {
     uint32_t layout;   // UMMA smem layout type
     int wpre_smem;     // bytes of one staged border-table buffer (0: read the tables from global memory)
     int* err_flag;     // device int: set non-zero by the watchdog
+    // fused-quantize variant (1x1, stride 1): A is produced from the fp32 NCHW input inside the kernel
+    int tiles_per_img; // > 0: M tiles never straddle images (tile = image, 128-pixel block); 0: flat pixel tiling
+    const float* x;
+    const float* q_scale;
+    const float* q_zero;
+    const float* q_qmin;
+    const float* q_qmax;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -67,26 +79,33 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires, so a waiting
+// warp does not burn issue slots that the quantizer / epilogue warps of the same SM sub-partition need.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a lost arrival must not hang the GPU — after ~4 s the kernel flags the error and traps.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    long long t0 = 0;
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) {
-            if (err_flag) atomicExch(err_flag, code);
-            __threadfence_system();
-            __trap();
+        if ((++spins & 0xFFu) == 0) {  // look at the clock only every 256 wake-ups
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 8000000000ll) {
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
         }
     }
 }
@@ -105,6 +124,17 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
           "h"(off_w), "h"(off_h)
         : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z)
+                 : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
@@ -169,7 +199,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kFQ>
+__global__ void __launch_bounds__(kFQ ? kThreadsFq : kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
@@ -179,12 +210,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const ConvGeom& gm = prm.gm;
     const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
     const uint32_t a_bytes = kBM * KC, b_bytes = BN * KC, stage_bytes = a_bytes + b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)stages * stage_bytes);
+    uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [kXStages][KC][128] fp32
+    const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : 0u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)(kFQ ? kXStages : 0) * x_bytes);
     uint64_t* full = bars;                     // [stages]
     uint64_t* empty = bars + kMaxStages;       // [stages]
     uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
     uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+    uint64_t* xfull = bars + 2 * kMaxStages + 4;     // [kXStages]
+    uint64_t* xempty = xfull + kXStages;             // [kXStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kXStages);
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][3][256]
     int32_t* wpre_s = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][BN][(R+1)(S+1)]
 
@@ -197,12 +232,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int i = 0; i < stages; ++i) {
-            mbar_init(&full[i], 1);
+            mbar_init(&full[i], kFQ ? 1 + kFqWarps * 32 : 1);  // TMA expect_tx arrival (+ every quantizer thread)
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], kEpiWarps);
+        }
+        for (int i = 0; i < kXStages; ++i) {
+            mbar_init(&xfull[i], 1);
+            mbar_init(&xempty[i], kFqWarps * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -232,8 +271,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
-                            mbar_expect_tx(&full[stage], stage_bytes);
-                            tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
+                            if (kFQ) {
+                                mbar_expect_tx(&full[stage], b_bytes);
+                            } else {
+                                mbar_expect_tx(&full[stage], stage_bytes);
+                                tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
+                            }
                             tma_load_2d(sb, &tmap_b, &full[stage], (r * gm.S + s) * gm.Cp + cb * KC, n_tile * BN);
                             if (++stage == stages) { stage = 0; phase ^= 1; }
                         }
@@ -265,6 +308,87 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 umma_commit(&acc_full[buf]);  // accumulator complete
                 if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (kFQ && warp == 2 + kEpiWarps) {
+        // ===================== TMA producer of the fp32 input tiles (fused-quantize variant) =====================
+        if (lane == 0) {
+            // The shared-memory ring holds only kXStages tiles; HBM latency is covered by prefetching the tiles of the
+            // next kPrefetch k-blocks into L2 (the ring loads then hit L2).
+            constexpr int kPrefetch = 0;   // measured: prefetching 10 k-blocks ahead thrashes L2 (1.7x DRAM reads); the ring alone is better
+            int pf_tile = blockIdx.x, pf_cb = 0;
+            auto prefetch_next = [&]() {
+                if (pf_tile >= total_tiles) return;
+                const int m_tile = pf_tile / prm.n_tiles;
+                const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                tma_prefetch_3d(&tmap_a, t * kBM, pf_cb * KC, img);
+                if (++pf_cb == prm.cblocks) { pf_cb = 0; pf_tile += gridDim.x; }
+            };
+            for (int i = 0; i < kPrefetch; ++i) prefetch_next();
+            uint32_t kbg = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m_tile = tile / prm.n_tiles;
+                const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                for (int cb = 0; cb < prm.cblocks; ++cb, ++kbg) {
+                    prefetch_next();
+                    const int xs = (int)(kbg % kXStages);
+                    const uint32_t xphase = (kbg / kXStages) & 1u;
+                    mbar_wait(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
+                    mbar_expect_tx(&xfull[xs], x_bytes);
+                    // box [128 pixels][KC channels] of image img; pixels beyond H*W are zero-filled
+                    tma_load_3d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], t * kBM, cb * KC, img);
+                }
+            }
+        }
+    } else if (kFQ && warp > 2 + kEpiWarps) {
+        // ===================== quantizer warps (fused-quantize variant: 1x1 / stride 1) =====================
+        // fp32 tile [KC channels][128 pixels] in shared memory -> u8 A tile [128 pixels][KC] in the swizzled K-major
+        // layout the MMA reads.  A thread owns 4 consecutive pixels x 8 channels (8 conflict-free 16-byte loads),
+        // quantizes them exactly like the standalone quantizer (quant_math.cuh) and stores four 8-byte channel vectors.
+        const QuantParams qp = load_params(prm.q_scale, prm.q_zero, prm.q_qmin, prm.q_qmax);
+        // All quantizer warps work on the same k-block (every barrier sees every phase: no parity aliasing):
+        // warp pw owns channels [8*pw, 8*pw + 8) of the 64-channel k-block for all 128 pixels.
+        const int pw = warp - (3 + kEpiWarps);
+        const int j16 = pw >> 1;          // 16-byte channel chunk of the A row this warp contributes to
+        const int half = pw & 1;          // which 8 bytes of that chunk
+        const int rot = lane >> 1;
+        uint32_t kbg = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int cb = 0; cb < prm.cblocks; ++cb, ++kbg) {
+                const int xs = (int)(kbg % kXStages);
+                const uint32_t xphase = (kbg / kXStages) & 1u;
+                const int stage = (int)(kbg % (uint32_t)stages);
+                const uint32_t phase = (kbg / (uint32_t)stages) & 1u;
+                mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
+                const float4* xt = reinterpret_cast<const float4*>(xring + (size_t)xs * x_bytes) + (pw * 8) * (kBM / 4) + lane;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = xt[i * (kBM / 4)];
+                uint32_t w[4][2];  // [pixel][word]
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    w[0][k] = quant_word(v[4 * k].x, v[4 * k + 1].x, v[4 * k + 2].x, v[4 * k + 3].x, qp);
+                    w[1][k] = quant_word(v[4 * k].y, v[4 * k + 1].y, v[4 * k + 2].y, v[4 * k + 3].y, qp);
+                    w[2][k] = quant_word(v[4 * k].z, v[4 * k + 1].z, v[4 * k + 2].z, v[4 * k + 3].z, qp);
+                    w[3][k] = quant_word(v[4 * k].w, v[4 * k + 1].w, v[4 * k + 2].w, v[4 * k + 3].w, qp);
+                }
+                mbar_arrive(&xempty[xs]);  // this thread's part of the fp32 tile is in registers
+                mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                // lanes rotate which of their 4 pixels they store in each step so that one store instruction spreads
+                // over all swizzle phases; SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int px = (t + rot) & 3;
+                    uint2 val;
+                    val.x = px == 0 ? w[0][0] : px == 1 ? w[1][0] : px == 2 ? w[2][0] : w[3][0];
+                    val.y = px == 0 ? w[0][1] : px == 1 ? w[1][1] : px == 2 ? w[2][1] : w[3][1];
+                    const int row = lane * 4 + px;
+                    const int jj = j16 ^ ((row >> 1) & 3);
+                    *reinterpret_cast<uint2*>(sa + row * kFqKC + (jj << 4) + (half << 3)) = val;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
+                mbar_arrive(&full[stage]);
             }
         }
     } else {
@@ -312,10 +436,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 epi_barrier();
             }
-            const int64_t m = (int64_t)m_tile * kBM + row;
-            const bool row_ok = m < prm.M;
-            const int img = row_ok ? (int)(m / PQ) : 0;
-            const int pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
+            bool row_ok;
+            int img, pq;
+            if (kFQ) {  // tiles never straddle images
+                img = m_tile / prm.tiles_per_img;
+                pq = (m_tile - img * prm.tiles_per_img) * kBM + row;
+                row_ok = pq < PQ;
+                if (!row_ok) pq = 0;
+            } else {
+                const int64_t m = (int64_t)m_tile * kBM + row;
+                row_ok = m < prm.M;
+                img = row_ok ? (int)(m / PQ) : 0;
+                pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
+            }
             const int p = pq / g.Q, q = pq - p * g.Q;
             const PixelWindow pw = pixel_window(g, p, q);
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
@@ -438,18 +571,20 @@ const DriverApi& driver_api() {
     return api;
 }
 
+// Watchdog flag in mapped pinned host memory: still readable after a trap has poisoned the context.
+int* g_watchdog_host = nullptr;
 int* watchdog_flag() {
-    // one device int per (thread, device); leaked on purpose (process lifetime)
-    static thread_local int* flags[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!flags[dev]) {
-        int* p = nullptr;
-        if (cudaMalloc(&p, sizeof(int)) != cudaSuccess) return nullptr;
-        cudaMemset(p, 0, sizeof(int));
-        flags[dev] = p;
+    static int* dev_ptr = nullptr;
+    if (!dev_ptr) {
+        int* h = nullptr;
+        if (cudaHostAlloc(&h, sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) return nullptr;
+        *h = 0;
+        int* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) != cudaSuccess) return nullptr;
+        g_watchdog_host = h;
+        dev_ptr = d;
     }
-    return flags[dev];
+    return dev_ptr;
 }
 
 int num_sms() {
@@ -467,6 +602,8 @@ int num_sms() {
 
 }  // namespace
 
+int watchdog_code() { return g_watchdog_host ? *(volatile int*)g_watchdog_host : 0; }
+
 bool umma_supported(const ConvGeom& g) {
     if (g.groups != 1) return false;
     if (g.pad > 128 || g.pad - (g.R - 1) < -128 || g.pad - (g.S - 1) < -128) return false;  // im2col corner range
@@ -475,9 +612,25 @@ bool umma_supported(const ConvGeom& g) {
     return true;
 }
 
+bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
+    return umma_supported(g) && g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0 && (g.H * g.W) % 4 == 0 &&
+           g.C % 64 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
+}
+
+// Measured on B200 (profiles/README.md): the in-kernel quantizer (8 warps) sustains ~3.5 TB/s of fp32 input, the
+// standalone quantizer ~5.5 TB/s.  Fusing wins when the layer is output-heavy and large: one 64-channel k-block per
+// tile (C == 64) on feature maps of at least 28x28; everything else keeps the two-kernel path.
+bool umma_fused_quant_profitable(const ConvGeom& g) { return g.C == 64 && g.H * g.W >= 784; }
+
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st, int gemm_rows) {
+                     cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
+    const bool fq = x_fused != nullptr;
+    if (fq) {
+        QB_REQUIRE(umma_fused_quant_supported(g, x_fused) && gemm_rows == 0 && aq_fused && aq_fused->qmin && aq_fused->qmax,
+                   QB200_EINVAL, "conv_umma: layer not eligible for the fused-quantize kernel");
+        qa = reinterpret_cast<const uint8_t*>(x_fused);  // only used for alignment checks below
+    }
     ConvGeom gm = g;
     if (gemm_rows > 0) {  // materialised im2col rows: a 1x1 convolution over an [N, P, Q, gemm_rows] tensor
         gm.C = gm.Cg = gm.Cp = gm.Cgp = gemm_rows;
@@ -498,9 +651,10 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.ep = ep;
     prm.M = (int64_t)g.N * g.P * g.Q;
     if (prm.M == 0) return 0;
-    prm.KC = (gm.Cp % 128 == 0) ? 128 : (gm.Cp % 64 == 0) ? 64 : 32;
+    prm.KC = fq ? kFqKC : (gm.Cp % 128 == 0) ? 128 : (gm.Cp % 64 == 0) ? 64 : 32;
     prm.cblocks = gm.Cp / prm.KC;
-    prm.m_tiles = (int)ceil_div64(prm.M, kBM);
+    prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : 0;
+    prm.m_tiles = fq ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
@@ -510,7 +664,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
     const int tbl_bytes = BN * (g.R + 1) * (g.S + 1) * 4;
     prm.wpre_smem = (g.R * g.S > 1 && 2 * tbl_bytes <= kMaxWpreBytes) ? tbl_bytes : 0;
-    const size_t tail = kTailBytes + 2 * (size_t)prm.wpre_smem;
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wpre_smem + (fq ? (size_t)kXStages * kFqKC * kBM * 4 : 0);
     int stages = (int)((kSmemBudget - 1024 - tail) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
@@ -520,12 +674,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // instruction descriptor: D=s32, A=u8, B=s8|u8, both K-major, N>>3, M>>4
     prm.idesc = (2u << 4) | (0u << 7) | ((g.w_sign ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
     prm.err_flag = watchdog_flag();
+    prm.x = x_fused;
+    prm.q_scale = fq ? aq_fused->scale : nullptr;
+    prm.q_zero = fq ? aq_fused->zero : nullptr;
+    prm.q_qmin = fq ? aq_fused->qmin : nullptr;
+    prm.q_qmax = fq ? aq_fused->qmax : nullptr;
 
     const CUtensorMapSwizzle swz = prm.KC == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                  : prm.KC == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
     alignas(64) CUtensorMap tmap_a, tmap_b;
-    {
+    if (!fq) {
         // activations: (C, W, H, N) u8, im2col mode; base pixel of an output (p,q) is (q*stride - pad, p*stride - pad)
         cuuint64_t dims[4] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W, (cuuint64_t)gm.H, (cuuint64_t)gm.N};
         cuuint64_t strides[3] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W * gm.Cp, (cuuint64_t)gm.H * gm.W * gm.Cp};
@@ -554,14 +713,28 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     }
 
     const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + tail;
-    static thread_local size_t smem_set = 0;
-    if (smem > smem_set) {
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        smem_set = kSmemBudget;
+    static thread_local bool smem_set = false;
+    if (!smem_set) {
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        smem_set = true;
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
     const int grid = total_tiles < sms ? total_tiles : sms;
-    conv_umma_kernel<<<grid, kThreads, smem, st>>>(tmap_a, tmap_b, prm, out);
+    if (fq) {
+        // fp32 input as (pixels, channels, images); box = 128 pixels x 64 channels, no swizzle, zero fill past H*W
+        cuuint64_t dims[3] = {(cuuint64_t)g.H * g.W, (cuuint64_t)g.C, (cuuint64_t)g.N};
+        cuuint64_t strides[2] = {(cuuint64_t)g.H * g.W * 4, (cuuint64_t)g.C * g.H * g.W * 4};
+        cuuint32_t box[3] = {(cuuint32_t)kBM, (cuuint32_t)kFqKC, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = api.tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x_fused), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(fp32 input) failed with CUresult %d", (int)r);
+        conv_umma_kernel<true><<<grid, kThreadsFq, smem, st>>>(tmap_a, tmap_b, prm, out);
+    } else {
+        conv_umma_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap_b, prm, out);
+    }
     QB_LAUNCH_CHECK();
     return 0;
 }

@@ -13,7 +13,7 @@ from gpu_util import (ActQ, c_act_quantize, c_conv_fused, c_prepare, c_weightonl
 from quantize_b200 import capi
 
 pytestmark = pytest.mark.gpu
-ALGOS = {"direct": capi.ALGO_DIRECT, "umma": capi.ALGO_UMMA}
+ALGOS = {"direct": capi.ALGO_DIRECT, "umma": capi.ALGO_UMMA_FUSED_QUANT, "umma2k": capi.ALGO_UMMA_TWO_KERNELS}
 
 
 def assert_close_1e3(got, ref):
@@ -65,6 +65,45 @@ def test_act_quantize_bit_exact(shape):
         assert not q[..., C:].any()          # padded channels are zero
 
 
+def test_act_quantize_rounding_boundaries_exact():
+    """The kernel replaces the IEEE divide by a reciprocal + two exact-residual corrections; the integers must still
+    be those of fl(fl(x/s) - z) rounded half-even.  Probe every rounding boundary k + 0.5 of every quantization
+    step with the inputs on it and a few ulps around it, for awkward scales / zero points, plus special values."""
+    rng = np.random.default_rng(2024)
+    cases = [(0.0371, -107.9, 0, 255), (1.0 / 3.0, -8.164, 0, 15), (0.013, -129.283, 0, 255), (1.0, 0.0, 0, 255),
+             (np.float32(1.9999999), 0.5, 0, 255), (np.float32(1.1754944e-3), -0.25, 0, 127), (3.0e-5, 17.3, 3, 200)]
+    cases += [(float(np.float32(rng.uniform(1e-4, 10))), float(np.float32(rng.uniform(-200, 50))), 0, 255) for _ in range(6)]
+    for (s, z, lo, hi) in cases:
+        s32, z32 = np.float32(s), np.float32(z)
+        k = np.arange(lo - 3, hi + 4, dtype=np.float64)
+        xs = []
+        for frac in (0.5, 0.0, 0.25, 0.499999, 0.500001):
+            base = ((k + frac + np.float64(z32)) * np.float64(s32)).astype(np.float32)
+            for ulps in range(-4, 5):
+                v = base.copy()
+                for _ in range(abs(ulps)):
+                    v = np.nextafter(v, np.float32(np.inf if ulps > 0 else -np.inf))
+                xs.append(v)
+        specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 3.4e38, -3.4e38, 1e-40, -1e-40, 1e-30, 123456.7],
+                            dtype=np.float32)
+        x = np.concatenate(xs + [specials, (rng.standard_normal(1 << 16) * 50).astype(np.float32)])
+        pad = (-x.size) % 64
+        x = np.concatenate([x, np.zeros(pad, np.float32)]).reshape(1, 16, -1, 4)      # H*W % 4 == 0: vector kernel
+        aq = ActQ(s, z, lo, hi)
+        want = oracle.act_quantize(x, float(s32), float(z32), lo, hi)
+        finite = ~np.isnan(x)                                  # NaN has no defined image (the kernel maps it to qmin)
+        want = np.where(finite, want, lo).astype(np.uint8)
+        got = c_act_quantize(torch.from_numpy(x).cuda(), aq).cpu().numpy()[..., :16].transpose(0, 3, 1, 2)
+        bad = got != want
+        assert not bad.any(), (s, z, x[bad][:5], got[bad][:5], want[bad][:5])
+        # the generic (non-vector) kernel through an odd spatial size
+        xo = x.reshape(-1)[: 16 * 49 * 3].reshape(3, 16, 7, 7).copy()
+        wo = oracle.act_quantize(xo, float(s32), float(z32), lo, hi)
+        wo = np.where(~np.isnan(xo), wo, lo).astype(np.uint8)
+        go = c_act_quantize(torch.from_numpy(xo).cuda(), aq).cpu().numpy()[..., :16].transpose(0, 3, 1, 2)
+        assert np.array_equal(go, wo)
+
+
 def test_act_quantize_ties_round_half_even():
     # x/s - z lands exactly on .5: torch.round and rintf both round half to even (quantizer.py:31)
     x = (np.arange(0, 64, dtype=np.float32) + 0.5).reshape(1, 1, 8, 8)
@@ -87,11 +126,11 @@ def fixture_case(name):
                 stride=f["stride"], pad=f["pad"], groups=f["groups"]), f
 
 
-@pytest.mark.parametrize("algo", ["direct", "umma"])
+@pytest.mark.parametrize("algo", ["direct", "umma", "umma2k"])
 @pytest.mark.parametrize("name", conv_fixture_names())
 def test_reference_fixture(name, algo):
     c, f = fixture_case(name)
-    if algo == "umma" and c["groups"] != 1:
+    if algo != "direct" and c["groups"] != 1:
         pytest.skip("tensor-core kernel is groups == 1; depthwise runs on the CUDA-core kernel")
     acc, out = run_case(c, ALGOS[algo])
     qa, acc_ref, out_ref = oracle_case(c)
@@ -121,14 +160,18 @@ SYNTH = [
     (2, 64, 9, 9, 128, 5, 1, 2, 1, 5, 7, True, False, False),      # 5x5, odd bit widths
     (1, 16, 6, 6, 8, 3, 1, 0, 1, 8, 8, True, False, False),        # no padding
     (4, 2048, 7, 7, 64, 1, 1, 0, 1, 8, 8, True, True, False),      # long K (16 k-blocks of 128)
+    (3, 256, 14, 14, 64, 1, 1, 0, 1, 8, 8, True, False, False),    # 1x1 single-kernel path, KC=128, z_a != 0, ragged M
+    (2, 512, 28, 28, 128, 1, 1, 0, 1, 8, 8, True, True, False),    # 1x1 single-kernel path, 4 k-blocks, both groups
+    (5, 64, 6, 6, 96, 1, 1, 0, 1, 4, 4, True, False, True),        # 1x1 single-kernel path, KC=64, A4, ragged K
+    (2, 192, 8, 8, 32, 1, 1, 0, 1, 8, 8, True, False, False),      # 1x1, C % 128 == 64 (KC=64, 3 k-blocks)
 ]
 
 
-@pytest.mark.parametrize("algo", ["direct", "umma"])
+@pytest.mark.parametrize("algo", ["direct", "umma", "umma2k"])
 @pytest.mark.parametrize("cfg", SYNTH, ids=lambda c: "N{}C{}H{}W{}K{}R{}s{}p{}g{}w{}a{}{}{}{}".format(*c[:11], "s" if c[11] else "u", "r" if c[12] else "", "t" if c[13] else ""))
 def test_synthetic_vs_oracle(cfg, algo):
     N, C, H, W, K, R, stride, pad, groups, wb, ab, wsign, relu, pt = cfg
-    if algo == "umma" and groups != 1:
+    if algo != "direct" and groups != 1:
         pytest.skip("tensor-core kernel is groups == 1")
     c = random_conv_case(hash(cfg) % (2 ** 31), N, C, H, W, K, R, stride, pad, groups, wb, ab, wsign, relu, pt)
     acc, out = run_case(c, ALGOS[algo])
