@@ -334,7 +334,7 @@ def run_b200(args):
         torch.cuda.empty_cache()
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-        net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0)
+        net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0, fuse_blocks=True)
         hw = models.INPUT_HW[args.model]
         host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
         host_out = torch.empty(args.batch, 1000, dtype=torch.float32).pin_memory()
@@ -380,7 +380,8 @@ def run_b200(args):
         e2e = {"value": round(args.batch * n_gpus / (e_ms / K / 1e3), 1), "unit": "images/s",
                "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                "ms_per_step": round(e_ms / K, 3), "wall_ms_per_step": round(wall / K * 1e3, 3),
-               "api": "models.build_packed(resnet50) forward: host.QuantConv2d -> quant_engine.quantconv2d_float_input",
+               "api": "models.build_packed(resnet50, fuse_blocks=True) forward: host.QuantConv2d -> quant_engine.quantconv2d_float_input "
+                      "(ReLU / residual add of each block run in the conv epilogues)",
                "pipelining": "H2D of step k+1 (copy stream, double buffer) overlaps the forward of step k; all copies inside the timed region",
                "engine_launches_per_step": int(L.qb200_launch_count()) // K}
 

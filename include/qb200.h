@@ -152,6 +152,18 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
                             const qb200_act_quant* aq, void* workspace, void* out, int32_t out_kind,
                             void* stream);
 
+/* Optional fused tail — an extension beyond the reference op for callers that own the surrounding graph (ResNet
+ * blocks): out = relu(out + residual), each step rounded as the separate fp32 ops would.  residual: device fp32
+ * [N,K,P,Q] or NULL; relu: 0/1.  With tail == NULL the call is exactly qb200_quantconv2d_fused. */
+typedef struct {
+    const float* residual;
+    int32_t relu;
+} qb200_conv_tail;
+int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const void* prepared,
+                               const float* w_scale, int32_t n_w_scale, const float* bias,
+                               const qb200_act_quant* aq, const qb200_conv_tail* tail, void* workspace, void* out,
+                               int32_t out_kind, void* stream);
+
 /* 1 when qb200_quantconv2d_fused runs this layer as ONE kernel (the quantizer runs in the conv kernel's producer warps
  * and no workspace is written), else 0.  Supported for 1x1, stride 1, pad 0, C % 64 == 0, H*W % 4 == 0, 16-byte
  * aligned x; chosen by default where it was measured to win (C == 64, feature map >= 28x28). */

@@ -17,6 +17,7 @@ SYMBOLS = [
     "qb200_conv_workspace_bytes", "qb200_act_quantize_nhwc", "qb200_set_conv_algo", "qb200_get_conv_algo",
     "qb200_quantconv2d_fused", "qb200_conv2d_q8_nhwc", "qb200_quantconv2d_weightonly",
     "qb200_conv_quantize_input", "qb200_conv_from_workspace", "qb200_conv_is_single_kernel", "qb200_watchdog_code",
+    "qb200_quantconv2d_fused_ex",
 ]
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
@@ -31,6 +32,10 @@ class ConvShape(ctypes.Structure):
 
 class ActQuant(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("scale", "zero", "qmin", "qmax")]
+
+
+class ConvTail(ctypes.Structure):
+    _fields_ = [("residual", ctypes.c_void_p), ("relu", ctypes.c_int32)]
 
 
 class Qb200Error(RuntimeError):
@@ -70,6 +75,7 @@ def lib():
         L.qb200_set_conv_algo.restype = None
         L.qb200_get_conv_algo.restype = ctypes.c_int
         L.qb200_quantconv2d_fused.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, vp, i32, vp]
+        L.qb200_quantconv2d_fused_ex.argtypes = [sp, vp, vp, vp, i32, vp, ap, ctypes.POINTER(ConvTail), vp, vp, i32, vp]
         L.qb200_conv2d_q8_nhwc.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, i32, vp]
         L.qb200_conv_is_single_kernel.argtypes = [sp, vp]
         L.qb200_conv_quantize_input.argtypes = [sp, vp, ap, vp, vp]

@@ -35,7 +35,7 @@ int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_qu
 // from_ws: `q` is the workspace written by quantize_input (layout per workspace_is_im2col); else NHWC(Cp) bytes
 int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const void* prepared, const float* w_scale,
              int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* out, int32_t out_kind, cudaStream_t st,
-             const float* x_fused = nullptr) {
+             const float* x_fused = nullptr, const qb200_conv_tail* tail = nullptr) {
     QB_REQUIRE(n_w_scale == 1 || n_w_scale == s->K, QB200_EINVAL, "weight_scale must have 1 or K elements");
     QB_REQUIRE(out_kind == QB200_OUT_F32 || out_kind == QB200_OUT_ACC, QB200_EINVAL, "conv: bad out_kind");
     QB_REQUIRE(aq && aq->scale && aq->zero, QB200_EINVAL, "conv: activation quantizer parameters missing");
@@ -51,6 +51,10 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     ep.wpre = reinterpret_cast<const int32_t*>(wq + L.wpre_off);
     ep.per_tensor_w = n_w_scale == 1;
     ep.out_kind = out_kind;
+    ep.residual = tail ? tail->residual : nullptr;
+    ep.relu = tail ? (tail->relu != 0) : 0;
+    QB_REQUIRE(out_kind == QB200_OUT_F32 || (!ep.residual && !ep.relu), QB200_EINVAL,
+               "conv: the fused tail applies to the fp32 output only");
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(g, q, wq, ep, out, st);
@@ -100,19 +104,27 @@ int qb200_conv_from_workspace(const qb200_conv_shape* s, const void* workspace, 
                     static_cast<cudaStream_t>(stream));
 }
 
-int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
-                            int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* workspace, void* out,
-                            int32_t out_kind, void* stream) {
+int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
+                               int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, const qb200_conv_tail* tail,
+                               void* workspace, void* out, int32_t out_kind, void* stream) {
     using namespace qb200;
     if (int rc = validate_shape(s)) return rc;
     if (s->N == 0) return 0;
     QB_REQUIRE(workspace != nullptr, QB200_EINVAL, "conv: workspace missing (qb200_conv_workspace_bytes)");
     QB_REQUIRE(x != nullptr, QB200_EINVAL, "conv: null input");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (single_kernel(make_geom(*s), x))
-        return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x);
+    // (a residual tail needs 32 more live registers in the epilogue than the 608-thread fused-quantize kernel has)
+    if (single_kernel(make_geom(*s), x) && !(tail && tail->residual))
+        return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x, tail);
     if (int rc = quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), st)) return rc;
-    return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st);
+    return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st,
+                    nullptr, tail);
+}
+
+int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
+                            int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, void* workspace, void* out,
+                            int32_t out_kind, void* stream) {
+    return qb200_quantconv2d_fused_ex(s, x, prepared, w_scale, n_w_scale, bias, aq, nullptr, workspace, out, out_kind, stream);
 }
 
 }  // extern "C"

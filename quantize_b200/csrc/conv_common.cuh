@@ -50,6 +50,9 @@ struct EpilogueParams {
     const int32_t* wpre;    // device, [K][R+1][S+1]
     int per_tensor_w;
     int out_kind;
+    // optional fused tail (extension beyond the reference op): out = relu(out + residual)
+    const float* residual;  // device, same shape as out, or null
+    int relu;
 };
 
 struct EpilogueScalars {
@@ -92,7 +95,14 @@ __device__ __forceinline__ float dequant_one(int32_t acc, int k, const ConvGeom&
     if (es.z_a != 0.f) t = __fmaf_rn(es.z_a, (float)window_wsum(ep.wpre, k, g.R, g.S, pw), t);
     const float sw = __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k));
     const float b = ep.bias ? __ldg(ep.bias + k) : 0.f;
-    return __fmaf_rn(__fmul_rn(es.s_a, sw), t, b);
+    float r = __fmaf_rn(__fmul_rn(es.s_a, sw), t, b);
+    return r;
+}
+
+__device__ __forceinline__ float epilogue_tail(float r, int64_t idx, const EpilogueParams& ep) {
+    if (ep.residual) r = __fadd_rn(r, __ldg(ep.residual + idx));
+    if (ep.relu) r = fmaxf(r, 0.f);
+    return r;
 }
 
 int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,

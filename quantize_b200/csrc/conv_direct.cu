@@ -57,7 +57,7 @@ conv_q8_direct_kernel(const uint8_t* __restrict__ qa, const uint8_t* __restrict_
     } else {
         const EpilogueScalars es = load_epilogue_scalars(ep);
         const PixelWindow pw = pixel_window(g, p, q);
-        static_cast<float*>(out)[idx] = dequant_one(acc, k, g, ep, es, pw);
+        static_cast<float*>(out)[idx] = epilogue_tail(dequant_one(acc, k, g, ep, es, pw), idx, ep);
     }
 }
 

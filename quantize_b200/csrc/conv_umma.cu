@@ -23,6 +23,8 @@
 
 #include <cuda.h>
 
+#include <type_traits>
+
 namespace qb200 {
 namespace {
 
@@ -465,46 +467,80 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride + half * cols);
             for (int c0 = 0; c0 < cols; c0 += 32) {
+                const int cc = half * cols + c0;  // first column of this chunk inside the tile
+                // optional fused tail (beyond the reference op): out = relu(out + residual), rounded like the separate
+                // torch ops (conv result rounded, then one add, then max).  The residual values of the whole chunk are
+                // requested before the accumulator is read, so their latency overlaps the TMEM load.
+                const int64_t o_off = o_base + (int64_t)cc * PQ;
+                const bool has_res = ep.residual != nullptr && !acc_out;
+                float rv[32];
+                if (has_res && row_ok) {
+                    const float* rs = ep.residual + o_off;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        rv[j] = (k_base + cc + j < g.K) ? __ldg(rs + (int64_t)j * PQ) : 0.f;
+                }
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 tmem_ld_wait();
-                const int cc = half * cols + c0;  // first column of this chunk inside the tile
                 if (!row_ok) continue;
+                const bool any_tail = has_res || ep.relu;
+                auto tail = [&](float val, int j) {
+                    if (has_res) val = __fadd_rn(val, rv[j]);
+                    if (ep.relu) val = fmaxf(val, 0.f);
+                    return val;
+                };
                 if (!acc_out && full_n && warp_interior) {
-                    float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
-                    // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias)
-                    if (es.z_a == 0.f) {
+                    float* o = static_cast<float*>(out) + o_off;
+                    // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
+                    // kTail is a compile-time switch so that the plain op pays nothing for the optional fused tail.
+                    auto fast = [&](auto kTailTag) {
+                        constexpr bool kTail = decltype(kTailTag)::value;
+                        if (es.z_a == 0.f) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                            const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
-                            o[0] = __fmaf_rn(s4.x, (float)(int32_t)v[j + 0], b4.x);
-                            o[PQ] = __fmaf_rn(s4.y, (float)(int32_t)v[j + 1], b4.y);
-                            o[2 * (int64_t)PQ] = __fmaf_rn(s4.z, (float)(int32_t)v[j + 2], b4.z);
-                            o[3 * (int64_t)PQ] = __fmaf_rn(s4.w, (float)(int32_t)v[j + 3], b4.w);
-                            o += 4 * (int64_t)PQ;
-                        }
-                    } else {
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+                                const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
+                                float r0 = __fmaf_rn(s4.x, (float)(int32_t)v[j + 0], b4.x);
+                                float r1 = __fmaf_rn(s4.y, (float)(int32_t)v[j + 1], b4.y);
+                                float r2 = __fmaf_rn(s4.z, (float)(int32_t)v[j + 2], b4.z);
+                                float r3 = __fmaf_rn(s4.w, (float)(int32_t)v[j + 3], b4.w);
+                                if (kTail) { r0 = tail(r0, j); r1 = tail(r1, j + 1); r2 = tail(r2, j + 2); r3 = tail(r3, j + 3); }
+                                const int64_t jo = (int64_t)j * PQ;
+                                o[jo] = r0;
+                                o[jo + PQ] = r1;
+                                o[jo + 2 * (int64_t)PQ] = r2;
+                                o[jo + 3 * (int64_t)PQ] = r3;
+                            }
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                            const float4 w4 = *reinterpret_cast<const float4*>(be + cc + j);
-                            const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
-                            o[0] = __fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x);
-                            o[PQ] = __fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y);
-                            o[2 * (int64_t)PQ] = __fmaf_rn(s4.z, __fmaf_rn(es.z_a, w4.z, (float)(int32_t)v[j + 2]), b4.z);
-                            o[3 * (int64_t)PQ] = __fmaf_rn(s4.w, __fmaf_rn(es.z_a, w4.w, (float)(int32_t)v[j + 3]), b4.w);
-                            o += 4 * (int64_t)PQ;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
+                                const float4 w4 = *reinterpret_cast<const float4*>(be + cc + j);
+                                const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
+                                float r0 = __fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x);
+                                float r1 = __fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y);
+                                float r2 = __fmaf_rn(s4.z, __fmaf_rn(es.z_a, w4.z, (float)(int32_t)v[j + 2]), b4.z);
+                                float r3 = __fmaf_rn(s4.w, __fmaf_rn(es.z_a, w4.w, (float)(int32_t)v[j + 3]), b4.w);
+                                if (kTail) { r0 = tail(r0, j); r1 = tail(r1, j + 1); r2 = tail(r2, j + 2); r3 = tail(r3, j + 3); }
+                                const int64_t jo = (int64_t)j * PQ;
+                                o[jo] = r0;
+                                o[jo + PQ] = r1;
+                                o[jo + 2 * (int64_t)PQ] = r2;
+                                o[jo + 3 * (int64_t)PQ] = r3;
+                            }
                         }
-                    }
+                    };
+                    if (any_tail) fast(std::true_type{});
+                    else fast(std::false_type{});
                 } else if (acc_out) {
-                    int32_t* o = static_cast<int32_t*>(out) + o_base + (int64_t)cc * PQ;
+                    int32_t* o = static_cast<int32_t*>(out) + o_off;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (k_base + cc + j < g.K) o[(int64_t)j * PQ] = (int32_t)v[j];
                 } else {
                     // ragged channel tile and / or border pixel of a layer with a non-zero activation zero point
-                    float* o = static_cast<float*>(out) + o_base + (int64_t)cc * PQ;
+                    float* o = static_cast<float*>(out) + o_off;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int k = k_base + cc + j;
@@ -518,7 +554,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             const float t = __fmaf_rn(es.z_a, (float)ws, (float)(int32_t)v[j]);
                             r = __fmaf_rn(sc[cc + j], t, br[cc + j]);
                         }
-                        o[(int64_t)j * PQ] = r;
+                        o[(int64_t)j * PQ] = tail(r, j);
                     }
                 }
             }

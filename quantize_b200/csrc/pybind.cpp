@@ -10,10 +10,11 @@
 //
 // Extension over the reference signature (keyword arguments, all optional):
 //   quantconv2d_float_input(..., stride, padding, input_scale=None, input_zero=None, input_qmin=None,
-//                           input_qmax=None)
+//                           input_qmax=None, residual=None, fuse_relu=False)
 // With the activation quantizer's parameters (Quantizer.scale/zero/qmin/qmax, modelzoo/modules/quantizer.py:119-123)
 // the op runs the fused activation-quantize + int8 tensor-core path; without them it computes the reference's
-// weight-only fp32 semantic.
+// weight-only fp32 semantic.  residual / fuse_relu fuse `relu(out + residual)` into the epilogue (bit-identical to the
+// separate torch ops) for callers that own the surrounding block.
 #include <pybind11/pybind11.h>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
@@ -227,7 +228,8 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
                                    const at::Tensor& weight_scale, const at::Tensor& weight_zero,
                                    const c10::optional<at::Tensor>& bias, const int stride, const int padding,
                                    const py::object& input_scale, const py::object& input_zero,
-                                   const py::object& input_qmin, const py::object& input_qmax) {
+                                   const py::object& input_qmin, const py::object& input_qmax,
+                                   const c10::optional<at::Tensor>& residual, const bool fuse_relu) {
     // same checks, same messages as quantconv2d_float_input.cu:151-159
     CHECK_INPUT(input);
     CHECK_FLOAT(input);
@@ -274,6 +276,13 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
     void* st = cur_stream();
 
     const bool fused = !input_scale.is_none();
+    TORCH_CHECK(fused || (!residual.has_value() && !fuse_relu),
+                "residual / fuse_relu need the activation quantizer parameters (the fused path)");
+    if (residual.has_value()) {
+        const at::Tensor& r = residual.value();
+        CHECK_INPUT(r);
+        TORCH_CHECK(r.dtype() == torch::kFloat32 && r.sizes() == out.sizes(), "residual must be a float tensor shaped like the output");
+    }
     if (!fused) {
         // the reference's semantic: no activation quantization, fp32 accumulate in the reference's order
         check_rc(qb200_quantconv2d_weightonly(&s, input.data_ptr<float>(), weight.data_ptr<uint8_t>(),
@@ -307,6 +316,7 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
         // asymmetric weights do not factor into an integer GEMM with a float zero point: fake-quantize the
         // activations on the device (quantizer.py:215-218) and run the fp32 weight-only kernel
         TORCH_CHECK(s.C == s.Cg, "asymmetric weights with groups > 1 are not supported");
+        TORCH_CHECK(!residual.has_value() && !fuse_relu, "residual / fuse_relu are not supported with asymmetric weights");
         auto f = [&](const py::object& o) {
             return THPVariable_Check(o.ptr()) ? THPVariable_Unpack(o.ptr()).detach().to(input.device(), at::kFloat).reshape({1})
                                               : at::full({1}, o.cast<double>(), input.options());
@@ -322,8 +332,11 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
     }
 
     auto ws = at::empty({(int64_t)qb200_conv_workspace_bytes(&s)}, weight.options());
-    check_rc(qb200_quantconv2d_fused(&s, input.data_ptr<float>(), pw->buffer.data_ptr(), weight_scale.data_ptr<float>(),
-                                     (int32_t)n_ws, bias_p, &aq, ws.data_ptr(), out.data_ptr(), QB200_OUT_F32, st),
+    qb200_conv_tail tail;
+    tail.residual = residual.has_value() ? residual.value().data_ptr<float>() : nullptr;
+    tail.relu = fuse_relu ? 1 : 0;
+    check_rc(qb200_quantconv2d_fused_ex(&s, input.data_ptr<float>(), pw->buffer.data_ptr(), weight_scale.data_ptr<float>(),
+                                        (int32_t)n_ws, bias_p, &aq, &tail, ws.data_ptr(), out.data_ptr(), QB200_OUT_F32, st),
              "quantconv2d_float_input");
     return out;
 }
@@ -368,7 +381,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("quantconv2d_float_input", &quantconv2d_float_input, "Quantized conv2d function with float input.",
           py::arg("input"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
           py::arg("bias"), py::arg("stride"), py::arg("padding"), py::arg("input_scale") = py::none(),
-          py::arg("input_zero") = py::none(), py::arg("input_qmin") = py::none(), py::arg("input_qmax") = py::none());
+          py::arg("input_zero") = py::none(), py::arg("input_qmin") = py::none(), py::arg("input_qmax") = py::none(),
+          py::arg("residual") = py::none(), py::arg("fuse_relu") = false);
     // engine-level helpers (not part of the reference surface)
     m.def("_launch_count", []() { return (uint64_t)qb200_launch_count(); });
     m.def("_launch_count_reset", []() { qb200_launch_count_reset(); });

@@ -180,6 +180,7 @@ class QuantConv2d(nn.Conv2d):
         self.calibrating = False
         self.packed = False
         self.use_engine = True
+        self.fuse_relu = False      # set by fuse_resnet_blocks: the ReLU that follows this conv runs in its epilogue
 
     def calibrate(self, x: Tensor):                                 # quantconv2d.py:141-152
         self.a_quantizer.calibrate(x.detach().clone())
@@ -205,18 +206,59 @@ class QuantConv2d(nn.Conv2d):
         self.w_quantizer = None
         self.packed = True
 
-    def forward(self, x: Tensor) -> Tensor:                         # quantconv2d.py:198-210
-        if not self.packed:
-            return self._forward(x)
-        a = self.a_quantizer
-        if self.use_engine:
+    def forward(self, x: Tensor, residual: Tensor = None) -> Tensor:    # quantconv2d.py:198-210
+        """`residual` / `self.fuse_relu` are this mirror's extension: out = relu(out + residual) in the conv's epilogue
+        (bit-identical to the separate torch ops, which is what every non-engine branch below executes)."""
+        if self.packed and self.use_engine:
+            a = self.a_quantizer
             return _engine.load().quantconv2d_float_input(
                 x.contiguous(), self.weight, self.w_des, self.w_scale, self.w_zero, self.bias, self.stride[0],
-                self.padding[0], input_scale=a.scale, input_zero=a.zero, input_qmin=a.qmin, input_qmax=a.qmax)
-        # the reference's packed forward, kept for cross-checks: float conv on dequantized operands
-        q, a_scale, a_zero = a.simulate(x)
-        w = _engine.load().tunpack(self.weight, self.w_des)
-        return self._conv_forward((q + a_zero).mul_(a_scale), (w + self.w_zero).mul_(self.w_scale), self.bias)
+                self.padding[0], input_scale=a.scale, input_zero=a.zero, input_qmin=a.qmin, input_qmax=a.qmax,
+                residual=None if residual is None else residual.contiguous(), fuse_relu=self.fuse_relu)
+        if not self.packed:
+            out = self._forward(x)
+        else:
+            # the reference's packed forward, kept for cross-checks: float conv on dequantized operands
+            q, a_scale, a_zero = self.a_quantizer.simulate(x)
+            w = _engine.load().tunpack(self.weight, self.w_des)
+            out = self._conv_forward((q + a_zero).mul_(a_scale), (w + self.w_zero).mul_(self.w_scale), self.bias)
+        if residual is not None:
+            out = out + residual
+        return torch.relu(out) if self.fuse_relu else out
+
+
+def _bottleneck_forward(self, x):
+    """torchvision.models.resnet.Bottleneck.forward with the ReLUs and the residual add folded into the convs."""
+    out = self.conv2(self.conv1(x))
+    identity = x if self.downsample is None else self.downsample(x)
+    return self.conv3(out, residual=identity)
+
+
+def _basicblock_forward(self, x):
+    """torchvision.models.resnet.BasicBlock.forward, same folding."""
+    out = self.conv1(x)
+    identity = x if self.downsample is None else self.downsample(x)
+    return self.conv2(out, residual=identity)
+
+
+def fuse_resnet_blocks(model):
+    """For torchvision ResNets rebuilt with QuantConv2d: run `relu` and `+ identity` in the conv epilogues.
+    Every fused conv applies relu(out [+ residual]) exactly where the original block does, so the network function is
+    unchanged (tests/test_models_gpu.py asserts bit-identical logits)."""
+    import types
+    import torchvision.models.resnet as R
+    for m in model.modules():
+        if isinstance(m, R.Bottleneck) and all(isinstance(c, QuantConv2d) for c in (m.conv1, m.conv2, m.conv3)):
+            for c in (m.conv1, m.conv2, m.conv3):
+                c.fuse_relu = True
+            m.forward = types.MethodType(_bottleneck_forward, m)
+        elif isinstance(m, R.BasicBlock) and all(isinstance(c, QuantConv2d) for c in (m.conv1, m.conv2)):
+            m.conv1.fuse_relu = m.conv2.fuse_relu = True
+            m.forward = types.MethodType(_basicblock_forward, m)
+    if isinstance(model, R.ResNet) and isinstance(model.conv1, QuantConv2d):
+        model.conv1.fuse_relu = True        # stem: conv1 -> (folded bn) -> relu -> maxpool
+        model.relu = nn.Identity()
+    return model
 
 
 def reconstruct(model: nn.Module, w_setting=None, a_setting=None) -> nn.Module:

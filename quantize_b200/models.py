@@ -92,11 +92,14 @@ def synthetic_batch(name, batch, seed=1, device="cpu"):
     return torch.randn(batch, 3, hw, hw, generator=g).to(device)
 
 
-def build_packed(name, w_bits=8, a_bits=8, calib_batch=8, device="cuda", seed=0):
-    """calibrate on a synthetic batch (one PTQ pass), pack every conv with the engine's tpack; ready for inference."""
+def build_packed(name, w_bits=8, a_bits=8, calib_batch=8, device="cuda", seed=0, fuse_blocks=False):
+    """calibrate on a synthetic batch (one PTQ pass), pack every conv with the engine's tpack; ready for inference.
+    fuse_blocks: fold ReLU / residual add of torchvision ResNet blocks into the conv epilogues (same function)."""
     model = build_quantized(name, w_bits, a_bits, seed).to(device)
     host.calibrate(model, synthetic_batch(name, calib_batch, seed + 1, device))
     host.pack(model)
+    if fuse_blocks:
+        host.fuse_resnet_blocks(model)
     return model
 
 

@@ -82,6 +82,45 @@ def test_mobilenet_v2_w4a8_depthwise_and_pointwise():
     _compare("mobilenet_v2", 4, 4, 8)
 
 
+@pytest.mark.parametrize("name,batch", [("resnet18", 4), ("resnet50", 2)])
+def test_fused_blocks_are_bit_identical(name, batch):
+    """relu / residual-add folded into the conv epilogues == the separate torch ops, bit for bit."""
+    model = models.build_packed(name, 8, 8, calib_batch=4)
+    x = models.synthetic_batch(name, batch, device="cuda")
+    with torch.no_grad():
+        want = model(x)
+        fused = host.fuse_resnet_blocks(copy.deepcopy(model))
+        assert sum(m.fuse_relu for m in host.quant_layers(fused)) >= 16
+        got = fused(x)
+        # and with the engine off (torch ops everywhere) the fused forward is still the same network
+        for m in host.quant_layers(fused):
+            m.use_engine = False
+        ref_path = fused(x)
+    assert torch.equal(got, want)
+    assert (ref_path - want).abs().max() <= 1e-2 * want.abs().max()
+    assert torch.equal(ref_path.argmax(1), want.argmax(1))
+
+
+def test_fused_tail_op_level(engine):
+    """quantconv2d_float_input(..., residual=, fuse_relu=) == relu(op(...) + residual), both conv kernels."""
+    from gpu_util import random_conv_case
+    import numpy as np
+    for cfg in ((2, 64, 14, 14, 64, 3, 1, 1, 1), (2, 64, 28, 28, 256, 1, 1, 0, 1), (2, 3, 33, 33, 64, 7, 2, 3, 1),
+                (2, 32, 8, 8, 32, 3, 1, 1, 32)):
+        N, C, H, W, K, R, stride, pad, groups = cfg
+        c = random_conv_case(sum(cfg), N, C, H, W, K, R, stride, pad, groups)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        kw = dict(input_scale=torch.tensor([c["a_scale"]]).cuda(), input_zero=torch.tensor([c["a_zero"]]).cuda(),
+                  input_qmin=0, input_qmax=255)
+        args = (t(c["x"]), t(c["packed"]), t(c["des"]), t(c["w_scale"]), torch.zeros(K).cuda(), t(c["bias"]), stride, pad)
+        base = engine.quantconv2d_float_input(*args, **kw)
+        res = torch.randn_like(base)
+        got = engine.quantconv2d_float_input(*args, **kw, residual=res, fuse_relu=True)
+        assert torch.equal(got, torch.relu(base + res))
+        assert torch.equal(engine.quantconv2d_float_input(*args, **kw, fuse_relu=True), torch.relu(base))
+        assert torch.equal(engine.quantconv2d_float_input(*args, **kw, residual=res), base + res)
+
+
 def test_batch_shards_equal_full_batch():
     """rows [k*B/G, (k+1)*B/G) of the full batch == the shard run on its own, bit for bit, for every
     conv of the network (the cuBLAS FC layer after the conv stack picks batch-dependent algorithms and is not ours)."""
