@@ -185,13 +185,20 @@ class ConvStack:
             max_out = max(max_out, s["N"] * s["K"] * P * Q)
             ops = 2 * s["N"] * s["K"] * P * Q * cg * s["R"] * s["R"]
             single = bool(self.L.qb200_conv_is_single_kernel(ctypes.byref(shape), x.data_ptr()))
+            # strided 1x1 layers only touch the sampled pixels; few-channel layers go through im2col rows
+            sub = s["R"] == 1 and s["stride"] > 1 and s["pad"] == 0
+            in_pix = s["N"] * (P * Q if sub else s["H"] * s["W"])
             w_bytes = s["K"] * s["R"] * s["R"] * Cp + 12 * s["K"]
             if single:   # one kernel: fp32 in, fp32 out
                 conv_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + w_bytes + 4 * s["N"] * s["K"] * P * Q
                 quant_bytes = 0
+            elif s["C"] <= 4 and s["R"] > 1:   # quantizer writes im2col rows [N*P*Q][Kcol]; the conv is a GEMM over them
+                kcol = (s["R"] * s["R"] * 4 + 127) // 128 * 128 if s["R"] * s["R"] * 4 > 64 else (64 if s["R"] * s["R"] * 4 > 32 else 32)
+                conv_bytes = s["N"] * P * Q * kcol + s["K"] * kcol + 12 * s["K"] + 4 * s["N"] * s["K"] * P * Q
+                quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * P * Q * kcol
             else:        # quantizer kernel (fp32 in, u8 out) + conv kernel (u8 in, fp32 out)
-                conv_bytes = s["N"] * s["H"] * s["W"] * Cp + w_bytes + 4 * s["N"] * s["K"] * P * Q
-                quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * s["H"] * s["W"] * Cp
+                conv_bytes = in_pix * Cp + w_bytes + 4 * s["N"] * s["K"] * P * Q
+                quant_bytes = 4 * s["C"] * in_pix + in_pix * Cp
             self.layers.append(dict(spec=s, x=x, shape=shape, prepared=prepared, aq=aq, aq_t=aq_t, w_scale=w_scale,
                                     bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed, single=single))
         self.ws = torch.empty(max_ws, dtype=torch.uint8, device=device)

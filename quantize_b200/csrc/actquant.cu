@@ -110,9 +110,12 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
 // ---------------------------------------------------------------------------------------------
 // generic kernel: any H*W / alignment.  thread = one pixel, scalar (still warp-coalesced) loads
 // ---------------------------------------------------------------------------------------------
+// sub > 1: only the pixels (p*sub, q*sub) of each image are quantized, into a compact [N, P, Q, Cp] buffer — what a
+// 1x1 convolution with stride `sub` and no padding reads (the other 1 - 1/sub^2 of the input is never touched).
 __global__ void __launch_bounds__(kThreads)
 act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C,
-                         int Cp, int HW, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                         int Cp, int HW, int sub, int W_in, int Q_out, int PQ_out,
+                         const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                          const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
     __shared__ uint4 tile[kPix * (kCw / 16)];
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
@@ -124,8 +127,17 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
     const int chunks = cw >> 4;
 
     if (g < total_pix) {
-        const int64_t n = g / HW;
-        const int pix = (int)(g - n * HW);
+        int64_t n;
+        int pix;
+        if (sub > 1) {
+            n = g / PQ_out;
+            const int po = (int)(g - n * PQ_out);
+            const int p = po / Q_out, qq = po - p * Q_out;
+            pix = p * sub * W_in + qq * sub;
+        } else {
+            n = g / HW;
+            pix = (int)(g - n * HW);
+        }
         const float* xp = x + (n * C + c_base) * (int64_t)HW + pix;
         for (int j = 0; j < chunks; ++j) {
             float v[16];
@@ -242,9 +254,26 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
     if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
         act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, aq->scale, aq->zero, aq->qmin, aq->qmax);
     else
-        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, aq->scale, aq->zero, aq->qmin, aq->qmax);
+        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, aq->scale, aq->zero,
+                                                             aq->qmin, aq->qmax);
     QB_LAUNCH_CHECK();
     return 0;
 }
 
 }  // extern "C"
+
+namespace qb200 {
+
+int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st) {
+    QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL,
+               "act_quantize: activation quantizer parameters missing");
+    QB_REQUIRE(g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1, QB200_EINVAL, "act_quantize_subsampled: not a strided 1x1 layer");
+    const int64_t total = (int64_t)g.N * g.P * g.Q;
+    dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
+    act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, g.H * g.W, g.stride, g.W, g.Q, g.P * g.Q,
+                                                         aq->scale, aq->zero, aq->qmin, aq->qmax);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace qb200

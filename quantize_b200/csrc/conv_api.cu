@@ -29,6 +29,7 @@ int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_qu
     const ConvGeom g = make_geom(*s);
     const PreparedLayout L = prepared_layout(*s);
     if (workspace_is_im2col(g, L)) return launch_act_quantize_im2col(x, g, L.Kcol, aq, ws, st);
+    if (uses_subsampled_input(g)) return launch_act_quantize_subsampled(x, g, aq, ws, st);
     return qb200_act_quantize_nhwc(x, s->N, s->C, s->H, s->W, aq, ws, st);
 }
 
@@ -57,8 +58,10 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
                "conv: the fused tail applies to the fp32 output only");
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
-    if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(g, q, wq, ep, out, st);
-    return launch_conv_direct(g, q, wq, ep, out, st);
+    // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
+    const ConvGeom gk = (from_ws && uses_subsampled_input(g)) ? subsampled_geom(g) : g;
+    if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(gk, q, wq, ep, out, st);
+    return launch_conv_direct(gk, q, wq, ep, out, st);
 }
 
 }  // namespace

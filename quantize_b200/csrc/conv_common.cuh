@@ -116,6 +116,16 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                      const qb200_act_quant* aq_fused = nullptr);
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x);
 bool umma_fused_quant_profitable(const ConvGeom& g);
+// 1x1 / stride > 1 / pad 0: quantize only the pixels the conv reads into a compact [N, P, Q, Cp] buffer
+int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);
+static inline bool uses_subsampled_input(const ConvGeom& g) { return g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1; }
+// the geometry the conv kernels see for such a layer: a stride-1 1x1 conv over the compact buffer
+static inline ConvGeom subsampled_geom(ConvGeom g) {
+    g.H = g.P;
+    g.W = g.Q;
+    g.stride = 1;
+    return g;
+}
 int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
                                cudaStream_t st);
 bool umma_supported(const ConvGeom& g);
