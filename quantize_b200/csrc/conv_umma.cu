@@ -37,7 +37,8 @@ constexpr int kXStages = 3;         // fp32 staging ring of the fused-quantize v
 constexpr int kFqKC = 64;           // its k-block: 64 channels (a 32 KB fp32 tile, an 8 KB u8 A tile)
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
 constexpr int kTailBytes = 256 + 2 * kConstFloats * 4;  // barriers + two constant buffers
-constexpr int kMaxWpreBytes = 2 * 16 * 1024;             // staged border tables (two buffers) for layers with R*S > 1
+constexpr int kMaxWclsBytes = 16 * 1024;                 // one buffer of per-window-class channel sums (layers with R*S > 1)
+constexpr int kMaxCls = 16;                              // distinct row (and column) windows supported by the class table
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
 constexpr int kMaxStages = 8;
@@ -56,7 +57,11 @@ struct UmmaParams {
     uint32_t idesc;
     uint32_t sbo16;    // stride-byte-offset >> 4 (8 rows * KC bytes)
     uint32_t layout;   // UMMA smem layout type
-    int wpre_smem;     // bytes of one staged border-table buffer (0: read the tables from global memory)
+    // Zero-point term of border pixels: the in-bounds tap window of an output pixel is one of n_rcls x n_ccls
+    // classes (rows x columns); the epilogue keeps sum(qw over the window) per (class, channel) in shared memory.
+    int wcls_smem;     // bytes of one class-table buffer (0: 4-corner lookups in the global prefix tables instead)
+    int n_rcls, n_ccls;
+    uint8_t rcls[kMaxCls][2], ccls[kMaxCls][2];   // [lo, hi) tap ranges
     int* err_flag;     // device int: set non-zero by the watchdog
     // fused-quantize variant (1x1, stride 1): A is produced from the fp32 NCHW input inside the kernel
     int tiles_per_img; // > 0: M tiles never straddle images (tile = image, 128-pixel block); 0: flat pixel tiling
@@ -223,7 +228,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* xempty = xfull + kXStages;             // [kXStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kXStages);
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][3][256]
-    int32_t* wpre_s = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][BN][(R+1)(S+1)]
+    float* wcls_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][n_cls][BN]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -416,13 +421,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             float* be = sc + 256;
             float* br = sc + 512;
             const int tbl = (g.R + 1) * (g.S + 1);
-            const int32_t* wtab = ep.wpre + (int64_t)k_base * tbl;  // border tables of this tile's channels
-            int kmax_tab = g.K - k_base;                            // rows of wtab that exist
+            const int32_t* wtab = ep.wpre + (int64_t)k_base * tbl;  // prefix tables of this tile's channels
+            const bool use_cls = prm.wcls_smem > 0 && es.z_a != 0.f;
+            float* wcls = wcls_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wcls_smem / 4);
             if (iter == 0 || prm.n_tiles > 1) {
-                if (prm.wpre_smem > 0 && es.z_a != 0.f) {
-                    int32_t* dst = wpre_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wpre_smem / 4);
-                    const int n_ent = min(BN, kmax_tab) * tbl;
-                    for (int i = et; i < n_ent; i += kEpiWarps * 32) dst[i] = __ldg(wtab + i);
+                if (use_cls) {
+                    const int s1c = g.S + 1;
+                    for (int i = et; i < prm.n_rcls * prm.n_ccls * BN; i += kEpiWarps * 32) {
+                        const int cls = i / BN, kk = i - cls * BN;
+                        float val = 0.f;
+                        if (k_base + kk < g.K) {
+                            const int rc = cls / prm.n_ccls, cx = cls - rc * prm.n_ccls;
+                            const int r0 = prm.rcls[rc][0], r1 = prm.rcls[rc][1], c0 = prm.ccls[cx][0], c1 = prm.ccls[cx][1];
+                            const int32_t* t4 = wtab + kk * tbl;
+                            val = (float)(__ldg(t4 + r1 * s1c + c1) - __ldg(t4 + r0 * s1c + c1) - __ldg(t4 + r1 * s1c + c0) +
+                                          __ldg(t4 + r0 * s1c + c0));
+                        }
+                        wcls[i] = val;
+                    }
                 }
                 if (et < BN) {
                     const int k = k_base + et;
@@ -454,11 +470,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int p = pq / g.Q, q = pq - p * g.Q;
             const PixelWindow pw = pixel_window(g, p, q);
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
-            // a warp with any border pixel computes the window form for all its lanes (no double execution)
+            // without a class table, a warp with any border pixel computes the window form for all its lanes
             const bool warp_interior = __all_sync(0xffffffffu, interior || !row_ok);
             const bool full_n = k_base + BN <= g.K;
-            const int32_t* wt = (prm.wpre_smem > 0 && es.z_a != 0.f)
-                                    ? wpre_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wpre_smem / 4) : wtab;
+            // this pixel's row of window sums: its class in the shared table, else the full-window sums
+            const float* wrow = be;
+            if (use_cls) {
+                int rc = 0, cx = 0;
+                for (int i = 0; i < prm.n_rcls; ++i)
+                    if (prm.rcls[i][0] == pw.r0 && prm.rcls[i][1] == pw.r1) rc = i;
+                for (int i = 0; i < prm.n_ccls; ++i)
+                    if (prm.ccls[i][0] == pw.s0 && prm.ccls[i][1] == pw.s1) cx = i;
+                wrow = wcls + (rc * prm.n_ccls + cx) * BN;
+            }
+            const bool uniform_ok = use_cls || warp_interior;
             const int s1 = g.S + 1;
             const int i11 = pw.r1 * s1 + pw.s1, i01 = pw.r0 * s1 + pw.s1, i10 = pw.r1 * s1 + pw.s0, i00 = pw.r0 * s1 + pw.s0;
             const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
@@ -490,7 +515,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (ep.relu) val = fmaxf(val, 0.f);
                     return val;
                 };
-                if (!acc_out && full_n && warp_interior) {
+                if (!acc_out && full_n && uniform_ok) {
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
                     // kTail is a compile-time switch so that the plain op pays nothing for the optional fused tail.
@@ -516,7 +541,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                                const float4 w4 = *reinterpret_cast<const float4*>(be + cc + j);
+                                const float4 w4 = *reinterpret_cast<const float4*>(wrow + cc + j);
                                 const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
                                 float r0 = __fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x);
                                 float r1 = __fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y);
@@ -549,9 +574,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (es.z_a == 0.f) {
                             r = __fmaf_rn(sc[cc + j], (float)(int32_t)v[j], br[cc + j]);
                         } else {
-                            const int32_t* t4 = wt + (cc + j) * tbl;
-                            const int32_t ws = t4[i11] - t4[i01] - t4[i10] + t4[i00];
-                            const float t = __fmaf_rn(es.z_a, (float)ws, (float)(int32_t)v[j]);
+                            float wsf;
+                            if (use_cls) {
+                                wsf = wrow[cc + j];
+                            } else {
+                                const int32_t* t4 = wtab + (cc + j) * tbl;
+                                wsf = (float)(__ldg(t4 + i11) - __ldg(t4 + i01) - __ldg(t4 + i10) + __ldg(t4 + i00));
+                            }
+                            const float t = __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]);
                             r = __fmaf_rn(sc[cc + j], t, br[cc + j]);
                         }
                         o[(int64_t)j * PQ] = tail(r, j);
@@ -698,9 +728,33 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.BN = BN;
     prm.n_tiles = (g.K + BN - 1) / BN;
     const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
-    const int tbl_bytes = BN * (g.R + 1) * (g.S + 1) * 4;
-    prm.wpre_smem = (g.R * g.S > 1 && 2 * tbl_bytes <= kMaxWpreBytes) ? tbl_bytes : 0;
-    const size_t tail = kTailBytes + 2 * (size_t)prm.wpre_smem + (fq ? (size_t)kXStages * kFqKC * kBM * 4 : 0);
+    // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
+    prm.wcls_smem = 0;
+    prm.n_rcls = prm.n_ccls = 0;
+    if (g.R * g.S > 1) {
+        auto classes = [&](int n_out, int in_dim, int taps, uint8_t (*dst)[2]) {
+            int n = 0;
+            for (int o = 0; o < n_out; ++o) {
+                const int h0 = o * g.stride - g.pad;
+                const int lo = h0 < 0 ? -h0 : 0, hi = taps < in_dim - h0 ? taps : in_dim - h0;
+                bool found = false;
+                for (int i = 0; i < n; ++i) found |= dst[i][0] == lo && dst[i][1] == hi;
+                if (found) continue;
+                if (n == kMaxCls) return -1;
+                dst[n][0] = (uint8_t)lo;
+                dst[n][1] = (uint8_t)hi;
+                ++n;
+            }
+            return n;
+        };
+        const int nr = classes(g.P, g.H, g.R, prm.rcls), nc = classes(g.Q, g.W, g.S, prm.ccls);
+        if (nr > 0 && nc > 0 && nr * nc * BN * 4 <= kMaxWclsBytes) {
+            prm.n_rcls = nr;
+            prm.n_ccls = nc;
+            prm.wcls_smem = nr * nc * BN * 4;
+        }
+    }
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (fq ? (size_t)kXStages * kFqKC * kBM * 4 : 0);
     int stages = (int)((kSmemBudget - 1024 - tail) / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
