@@ -163,55 +163,67 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
 
 // ---------------------------------------------------------------------------------------------
 // few-channel layers (RGB stem): quantize straight into im2col rows.
-// One block = one output row (n, p).  The R input rows it touches are quantized ONCE into a shared patch of packed
+// One block = 8 output rows of one image.  The input rows they touch are quantized ONCE into a shared patch of packed
 // words (one word = the <=4 channels of a pixel); pixels outside the image are 0, so that padded taps add nothing to
 // sum(qa*qw) — the reference skips them (quantconv2d_float_input.cu:92) and their zero-point term is excluded by the
 // border tables.  Then every output pixel's row of Kcol bytes (word r*S+s = patch[r][q*stride + s], remaining words 0)
 // is written with fully coalesced stores.
 // ---------------------------------------------------------------------------------------------
+constexpr int kIm2colRows = 8;  // output rows per block: (8-1)*stride + R input rows are quantized once and shared
+
 __global__ void __launch_bounds__(256)
 act_quantize_im2col_kernel(const float* __restrict__ x, uint32_t* __restrict__ a_col, ConvGeom g, int Kwords,
                            const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                            const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
-    extern __shared__ uint32_t patch[];  // [R][Wp], Wp = W + 2*pad
+    extern __shared__ uint32_t patch[];  // [rows_in][Wp], Wp = W + 2*pad
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
     const int Wp = g.W + 2 * g.pad;
-    const int n = blockIdx.x / g.P, po = blockIdx.x - n * g.P;
-    const int h0 = po * g.stride - g.pad;
+    const int pblocks = (g.P + kIm2colRows - 1) / kIm2colRows;
+    const int n = blockIdx.x / pblocks, p0 = (blockIdx.x - n * pblocks) * kIm2colRows;
+    const int n_out = min(kIm2colRows, g.P - p0);
+    const int rows_in = (n_out - 1) * g.stride + g.R;
+    const int h0 = p0 * g.stride - g.pad;
     const int HW = g.H * g.W;
-    for (int i = threadIdx.x; i < g.R * Wp; i += blockDim.x) {
-        const int r = i / Wp, j = i - r * Wp;
-        const int ih = h0 + r, iw = j - g.pad;
-        uint32_t word = 0;
-        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
-            const float* xp = x + (int64_t)n * g.C * HW + (int64_t)ih * g.W + iw;
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t keep = g.C >= 4 ? 0xFFFFFFFFu : (1u << (8 * g.C)) - 1u;
+    for (int r = warp; r < rows_in; r += 8) {
+        const int ih = h0 + r;
+        const bool row_in = ih >= 0 && ih < g.H;
+        const float* xr = x + (int64_t)n * g.C * HW + (int64_t)ih * g.W;
+        for (int j = lane; j < Wp; j += 32) {
+            const int iw = j - g.pad;
+            uint32_t word = 0;
+            if (row_in && iw >= 0 && iw < g.W) {
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-                if (c < g.C) a[c] = __ldg(xp + (int64_t)c * HW);
-            word = quant_word(a[0], a[1], a[2], a[3], p);
-            if (g.C < 4) word &= (1u << (8 * g.C)) - 1u;
+                for (int c = 0; c < 4; ++c)
+                    if (c < g.C) a[c] = __ldg(xr + (int64_t)c * HW + iw);
+                word = quant_word(a[0], a[1], a[2], a[3], p) & keep;
+            }
+            patch[r * Wp + j] = word;
         }
-        patch[i] = word;
     }
     __syncthreads();
     const int taps = g.R * g.S;
-    uint32_t* orow = a_col + ((int64_t)n * g.P + po) * g.Q * Kwords;
-    if (blockDim.x % Kwords == 0) {
-        // every thread owns one word position of the row for all the pixels it visits: no per-word division
-        const int wd = threadIdx.x % Kwords, q0 = threadIdx.x / Kwords, qstep = blockDim.x / Kwords;
-        const int r = wd / g.S;
-        const int off = (wd < taps) ? r * Wp + (wd - r * g.S) : -1;
-        for (int q = q0; q < g.Q; q += qstep) orow[q * Kwords + wd] = off >= 0 ? patch[off + q * g.stride] : 0u;
-    } else {
-        for (int i = threadIdx.x; i < g.Q * Kwords; i += blockDim.x) {
-            const int q = i / Kwords, wd = i - q * Kwords;
-            uint32_t v = 0;
-            if (wd < taps) {
-                const int r = wd / g.S, s = wd - r * g.S;
-                v = patch[r * Wp + q * g.stride + s];
+    for (int t = 0; t < n_out; ++t) {
+        uint32_t* orow = a_col + ((int64_t)n * g.P + p0 + t) * g.Q * Kwords;
+        const uint32_t* prow = patch + t * g.stride * Wp;
+        if (blockDim.x % Kwords == 0) {
+            // every thread owns one word position of the row for all the pixels it visits: no per-word division
+            const int wd = threadIdx.x % Kwords, q0 = threadIdx.x / Kwords, qstep = blockDim.x / Kwords;
+            const int r = wd / g.S;
+            const int off = (wd < taps) ? r * Wp + (wd - r * g.S) : -1;
+            for (int q = q0; q < g.Q; q += qstep) orow[q * Kwords + wd] = off >= 0 ? prow[off + q * g.stride] : 0u;
+        } else {
+            for (int i = threadIdx.x; i < g.Q * Kwords; i += blockDim.x) {
+                const int q = i / Kwords, wd = i - q * Kwords;
+                uint32_t v = 0;
+                if (wd < taps) {
+                    const int r = wd / g.S, s = wd - r * g.S;
+                    v = prow[r * Wp + q * g.stride + s];
+                }
+                orow[i] = v;
             }
-            orow[i] = v;
         }
     }
 }
@@ -223,9 +235,10 @@ int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, cons
     QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL,
                "act_quantize: activation quantizer parameters missing");
     QB_REQUIRE(g.C <= 4 && g.groups == 1 && Kcol >= g.R * g.S * 4, QB200_EINVAL, "act_quantize_im2col: not a few-channel layer");
-    const size_t smem = (size_t)g.R * (g.W + 2 * g.pad) * sizeof(uint32_t);
+    const size_t smem = (size_t)((kIm2colRows - 1) * g.stride + g.R) * (g.W + 2 * g.pad) * sizeof(uint32_t);
     QB_REQUIRE(smem <= 48 * 1024, QB200_EUNSUPPORTED, "act_quantize_im2col: input row too wide");
-    act_quantize_im2col_kernel<<<(unsigned)(g.N * g.P), 256, smem, st>>>(x, reinterpret_cast<uint32_t*>(a_col), g, Kcol / 4,
+    const int pblocks = (g.P + kIm2colRows - 1) / kIm2colRows;
+    act_quantize_im2col_kernel<<<(unsigned)(g.N * pblocks), 256, smem, st>>>(x, reinterpret_cast<uint32_t*>(a_col), g, Kcol / 4,
                                                                          aq->scale, aq->zero, aq->qmin, aq->qmax);
     QB_LAUNCH_CHECK();
     return 0;
