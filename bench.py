@@ -262,8 +262,10 @@ def run_b200(args):
     if args.layers:
         keep = [int(v) for v in args.layers.split(",")]
         specs = [specs[i] for i in keep]
-    stack = ConvStack(specs, device, seed=rank)
     L = capi.lib()
+    if os.environ.get("QB200_BENCH_ALGO"):               # A/B aid: 3 = plain two-kernel tensor-core path everywhere
+        L.qb200_set_conv_algo(int(os.environ["QB200_BENCH_ALGO"]))
+    stack = ConvStack(specs, device, seed=rank)
     stream_obj = torch.cuda.current_stream()
     stream = ctypes.c_void_p(stream_obj.cuda_stream)
 

@@ -37,14 +37,64 @@ __device__ __forceinline__ void copy_out(const uint4* tile, uint8_t* __restrict_
     }
 }
 
+// Zero-padded output for the halo path of the conv kernel: pixel (n,h,w) goes to row ((n*Hp + h + pad)*Wp + w + pad) of a
+// [N*Hp*Wp][Cp] matrix (Hp = H + 2*pad, Wp = W + 2*pad) and the pad pixels are written as zeros by the blocks that own
+// the neighbouring image-border pixels, so that the buffer never needs a separate memset.
+struct PadSpec {
+    int pad, H, W;
+};
+
+__device__ __forceinline__ void copy_out_padded(const uint4* tile, uint8_t* __restrict__ q, int64_t g0, int n_rows, int chunks,
+                                                int Cp, int c_base, const PadSpec ps, int* rowoff) {
+    const int Hp = ps.H + 2 * ps.pad, Wp = ps.W + 2 * ps.pad, HW = ps.H * ps.W;
+    const int t = threadIdx.x;
+    int n = 0, h = 0, w = 0;
+    if (t < n_rows) {
+        const int64_t g = g0 + t;
+        n = (int)(g / HW);
+        const int rem = (int)(g - (int64_t)n * HW);
+        h = rem / ps.W;
+        w = rem - h * ps.W;
+        rowoff[t] = (n * Hp + h + ps.pad) * Wp + w + ps.pad;
+    }
+    __syncthreads();
+    const int total = n_rows * chunks;
+    for (int i = t; i < total; i += kThreads) {
+        const int row = i / chunks, col = i - row * chunks;
+        const uint4 v = tile[row * (kCw / 16) + (col ^ (row & 7))];
+        *reinterpret_cast<uint4*>(q + (int64_t)rowoff[row] * Cp + c_base + col * 16) = v;
+    }
+    if (t < n_rows) {
+        // pad pixels adjacent to this pixel: left / right of its row; above / below its column (corners with the
+        // first / last pixel of the first / last row)
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        auto zero_px = [&](int hp, int wp) {
+            uint8_t* d = q + (int64_t)((n * Hp + hp) * Wp + wp) * Cp + c_base;
+            for (int c = 0; c < chunks; ++c) reinterpret_cast<uint4*>(d)[c] = z;
+        };
+        const int wlo = (w == 0) ? 0 : w + ps.pad, whi = (w == ps.W - 1) ? Wp : w + ps.pad + 1;  // column span incl. corners
+        if (w == 0)
+            for (int i = 0; i < ps.pad; ++i) zero_px(h + ps.pad, i);
+        if (w == ps.W - 1)
+            for (int i = 0; i < ps.pad; ++i) zero_px(h + ps.pad, ps.W + ps.pad + i);
+        if (h == 0)
+            for (int r = 0; r < ps.pad; ++r)
+                for (int c = wlo; c < whi; ++c) zero_px(r, c);
+        if (h == ps.H - 1)
+            for (int r = 0; r < ps.pad; ++r)
+                for (int c = wlo; c < whi; ++c) zero_px(ps.H + ps.pad + r, c);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // vector kernel: H*W % 4 == 0, x 16-byte aligned.  thread = (pixel quad, 16-channel group)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
 act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C, int Cp, int HW,
-                              const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                              const PadSpec ps, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                               const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
     __shared__ uint4 tile[kPix * (kCw / 16)];
+    __shared__ int rowoff[kPix];
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
     const int pq = threadIdx.x & 31;   // pixel quad inside the block
     const int cg = threadIdx.x >> 5;   // 16-channel group inside a 64-channel sub-pass (warp-uniform)
@@ -104,7 +154,8 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
     }
     __syncthreads();
     const int n_rows = (int)min((int64_t)kPix, total_pix - g0);
-    copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
+    if (ps.pad > 0) copy_out_padded(tile, q, g0, n_rows, chunks, Cp, c_base, ps, rowoff);
+    else copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -114,10 +165,11 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
 // 1x1 convolution with stride `sub` and no padding reads (the other 1 - 1/sub^2 of the input is never touched).
 __global__ void __launch_bounds__(kThreads)
 act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C,
-                         int Cp, int HW, int sub, int W_in, int Q_out, int PQ_out,
+                         int Cp, int HW, int sub, int W_in, int Q_out, int PQ_out, const PadSpec ps,
                          const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                          const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
     __shared__ uint4 tile[kPix * (kCw / 16)];
+    __shared__ int rowoff[kPix];
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
     const int t = threadIdx.x;
     const int64_t g0 = (int64_t)blockIdx.x * kPix;
@@ -158,7 +210,8 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
     }
     __syncthreads();
     const int n_rows = (int)min((int64_t)kPix, total_pix - g0);
-    copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
+    if (ps.pad > 0) copy_out_padded(tile, q, g0, n_rows, chunks, Cp, c_base, ps, rowoff);
+    else copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -264,10 +317,12 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
     const int64_t total = (int64_t)N * HW;
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((Cp + kCw - 1) / kCw));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PadSpec ps{0, H, W};
     if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
-        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, aq->scale, aq->zero, aq->qmin, aq->qmax);
+        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
+                                                                  aq->qmax);
     else
-        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, aq->scale, aq->zero,
+        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, ps, aq->scale, aq->zero,
                                                              aq->qmin, aq->qmax);
     QB_LAUNCH_CHECK();
     return 0;
@@ -284,7 +339,25 @@ int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb20
     const int64_t total = (int64_t)g.N * g.P * g.Q;
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
     act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, g.H * g.W, g.stride, g.W, g.Q, g.P * g.Q,
-                                                         aq->scale, aq->zero, aq->qmin, aq->qmax);
+                                                         PadSpec{0, g.H, g.W}, aq->scale, aq->zero, aq->qmin, aq->qmax);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+// zero-padded NHWC for the halo path: [N][H + 2*pad][W + 2*pad][Cp]
+int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st) {
+    QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL,
+               "act_quantize: activation quantizer parameters missing");
+    const int HW = g.H * g.W;
+    const int64_t total = (int64_t)g.N * HW;
+    dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
+    const PadSpec ps{g.pad, g.H, g.W};
+    if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
+        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
+                                                                  aq->qmax);
+    else
+        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, HW, 1, g.W, g.W, HW, ps, aq->scale, aq->zero,
+                                                             aq->qmin, aq->qmax);
     QB_LAUNCH_CHECK();
     return 0;
 }

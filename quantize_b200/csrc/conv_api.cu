@@ -21,6 +21,12 @@ bool single_kernel(const ConvGeom& g, const float* x) {
     return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_fused_quant_profitable(g);
 }
 
+// stride-1 spatial kernels: zero-padded workspace + one halo load per tile instead of one im2col load per tap
+bool workspace_is_padded(const ConvGeom& g) {
+    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || resolve_algo(g) != QB200_ALGO_UMMA || !umma_halo_supported(g)) return false;
+    return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_halo_profitable(g);   // algo 4 forces every variant (tests)
+}  // (umma_halo_supported implies the tap-major weight copy exists: spatial kernel, groups == 1, C > 4)
+
 // does the conv kernel chosen for this shape read materialised im2col rows (few-channel layers) or NHWC(Cp) bytes?
 bool workspace_is_im2col(const ConvGeom& g, const PreparedLayout& L) { return resolve_algo(g) == QB200_ALGO_UMMA && L.Kcol > 0; }
 
@@ -30,6 +36,7 @@ int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_qu
     const PreparedLayout L = prepared_layout(*s);
     if (workspace_is_im2col(g, L)) return launch_act_quantize_im2col(x, g, L.Kcol, aq, ws, st);
     if (uses_subsampled_input(g)) return launch_act_quantize_subsampled(x, g, aq, ws, st);
+    if (workspace_is_padded(g)) return launch_act_quantize_padded(x, g, aq, ws, st);
     return qb200_act_quantize_nhwc(x, s->N, s->C, s->H, s->W, aq, ws, st);
 }
 
@@ -59,6 +66,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
+    if (from_ws && workspace_is_padded(g) && L.tapKC) return launch_conv_umma(g, q, wq + L.wtap_off, ep, out, st, 0, nullptr, nullptr, true);
     const ConvGeom gk = (from_ws && uses_subsampled_input(g)) ? subsampled_geom(g) : g;
     if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(gk, q, wq, ep, out, st);
     return launch_conv_direct(gk, q, wq, ep, out, st);

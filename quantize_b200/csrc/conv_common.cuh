@@ -15,8 +15,13 @@ struct PreparedLayout {
     size_t wpre_off;
     int Kcol;          // bytes per row of the materialised-im2col weight matrix (0: layer does not use it)
     size_t wcol_off;
+    // tap-major copy for the halo variant: [cblocks][R*S][K][KC] (KC = the k-block width implied by Cgp), so that the
+    // weight tiles of several taps are ONE 3-D TMA box; present for spatial kernels with groups == 1 and C > 4
+    int tapKC;         // 0: absent
+    size_t wtap_off;
     size_t total;
 };
+static inline int kblock_bytes(int Cp) { return (Cp % 128 == 0) ? 128 : (Cp % 64 == 0) ? 64 : 32; }
 // Layers with very few input channels (the RGB stem) waste the tensor pipe and the TMA unit when channels are padded
 // to 32 per tap; for them the activation pass writes the im2col matrix itself (one 4-byte word per tap = the pixel's
 // <=4 channels) and the conv runs as a plain GEMM over Kcol "channels".
@@ -111,9 +116,13 @@ int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, 
 // then runs as a 1x1 convolution over it while the epilogue keeps the real geometry g.
 // x_fused != nullptr: 1x1 / stride-1 layer whose A operand is quantized inside the kernel from the fp32 NCHW input
 // (see umma_fused_quant_supported); qa is then ignored.
+// halo: qa is the zero-padded NHWC buffer written by launch_act_quantize_padded (see umma_halo_supported).
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows = 0, const float* x_fused = nullptr,
-                     const qb200_act_quant* aq_fused = nullptr);
+                     const qb200_act_quant* aq_fused = nullptr, bool halo = false);
+bool umma_halo_supported(const ConvGeom& g);
+bool umma_halo_profitable(const ConvGeom& g);
+int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x);
 bool umma_fused_quant_profitable(const ConvGeom& g);
 // 1x1 / stride > 1 / pad 0: quantize only the pixels the conv reads into a compact [N, P, Q, Cp] buffer

@@ -36,13 +36,35 @@ constexpr int kThreadsFq = kThreads + 32 + kFqWarps * 32;  // + one TMA warp for
 constexpr int kXStages = 3;         // fp32 staging ring of the fused-quantize variant
 constexpr int kFqKC = 64;           // its k-block: 64 channels (a 32 KB fp32 tile, an 8 KB u8 A tile)
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
-constexpr int kTailBytes = 256 + 2 * kConstFloats * 4;  // barriers + two constant buffers
+constexpr int kBarBytes = 512;                           // mbarriers + TMEM slot
+constexpr int kTailBytes = kBarBytes + 2 * kConstFloats * 4;  // barriers + two constant buffers
 constexpr int kMaxWclsBytes = 16 * 1024;                 // one buffer of per-window-class channel sums (layers with R*S > 1)
 constexpr int kMaxCls = 16;                              // distinct row (and column) windows supported by the class table
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;      // small stages (weight-only tiles of the halo variant) need depth to cover TMA latency
 constexpr size_t kSmemBudget = 200 * 1024;
+
+// Division of a non-negative 32-bit value by a launch-time constant as one multiply-high + shift: the per-tile index
+// arithmetic of the epilogue (tile -> image, row, column) otherwise costs ~40 instructions per division.
+struct FastDiv {
+    uint32_t mul, shift, d;
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shift); }
+};
+static FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (uint32_t)(d < 1 ? 1 : d);
+    f.mul = 0;
+    f.shift = 0;
+    if (f.d > 1) {
+        int lg = 0;
+        while ((1u << lg) < f.d) ++lg;                        // ceil(log2 d)
+        const int p = 31 + lg;                                // exact for 0 <= n < 2^31
+        f.mul = (uint32_t)((((unsigned __int128)1 << p) + f.d - 1) / f.d);
+        f.shift = (uint32_t)(p - 32);
+    }
+    return f;
+}
 
 struct UmmaParams {
     ConvGeom g;        // the convolution (epilogue: output addressing, border windows)
@@ -65,6 +87,14 @@ struct UmmaParams {
     int* err_flag;     // device int: set non-zero by the watchdog
     // fused-quantize variant (1x1, stride 1): A is produced from the fp32 NCHW input inside the kernel
     int tiles_per_img; // > 0: M tiles never straddle images (tile = image, 128-pixel block); 0: flat pixel tiling
+    // halo variant (stride 1, R*S > 1): activations are zero-padded NHWC [N][Hp][Wp][Cp]; an M tile is 128 consecutive
+    // positions of the padded-flat output grid and ONE 2-D TMA load of halo_rows rows serves every filter tap — tap
+    // (r,s) is the same shared-memory region read through a descriptor shifted by (r*Wp + s) rows
+    // (tests/native/desc_shift.cu shows the hardware swizzles on absolute addresses, so shifted descriptors are exact).
+    int halo;          // 0/1
+    int Hp, Wp, halo_rows, halo_bytes, h_stages;
+    FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
+    int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
     const float* x;
     const float* q_scale;
     const float* q_zero;
@@ -167,6 +197,18 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors given as (low word, shared high word)
+__device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
@@ -216,10 +258,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const ConvGeom& g = prm.g;
     const ConvGeom& gm = prm.gm;
     const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
-    const uint32_t a_bytes = kBM * KC, b_bytes = BN * KC, stage_bytes = a_bytes + b_bytes;
+    const bool halo = !kFQ && prm.halo != 0;
+    const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = BN * KC,
+                   stage_bytes = halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes;
     uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [kXStages][KC][128] fp32
-    const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : 0u;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)(kFQ ? kXStages : 0) * x_bytes);
+    const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u);  // ring slot size
+    const int x_slots = kFQ ? kXStages : (halo ? prm.h_stages : 0);       // fp32 tiles (kFQ) or u8 halo tiles (halo)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)x_slots * x_bytes);
     uint64_t* full = bars;                     // [stages]
     uint64_t* empty = bars + kMaxStages;       // [stages]
     uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
@@ -227,7 +272,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* xfull = bars + 2 * kMaxStages + 4;     // [kXStages]
     uint64_t* xempty = xfull + kXStages;             // [kXStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kXStages);
-    float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [2][3][256]
+    float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][3][256]
     float* wcls_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][n_cls][BN]
 
     const int warp = threadIdx.x >> 5;
@@ -248,7 +293,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < kXStages; ++i) {
             mbar_init(&xfull[i], 1);
-            mbar_init(&xempty[i], kFqWarps * 32);
+            mbar_init(&xempty[i], kFQ ? kFqWarps * 32 : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -264,7 +309,40 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             const int PQ = gm.P * gm.Q;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int hs = 0;
+            uint32_t hphase = 0;
+            if (halo) {
+                // Work items j = (tile, channel block).  The halo of item j+1 is requested BEFORE the weight tiles of
+                // item j: the weight ring is shallower than R*S taps, so the producer would otherwise only reach the
+                // next halo after this item's MMAs have started, exposing a full load latency per tile.
+                int h_tile = blockIdx.x, h_cb = 0;   // next halo to request
+                auto request_halo = [&]() {
+                    if (h_tile >= total_tiles) return;
+                    const int m_tile = h_tile / prm.n_tiles;
+                    const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                    const int f0 = img * prm.Hp * prm.Wp + t * kBM;   // first padded-flat position of the tile
+                    mbar_wait(&xempty[hs], hphase ^ 1, prm.err_flag, 6);
+                    mbar_expect_tx(&xfull[hs], (uint32_t)(prm.halo_rows * KC));
+                    tma_load_2d(xring + (size_t)hs * x_bytes, &tmap_a, &xfull[hs], h_cb * KC, f0);
+                    if (++hs == prm.h_stages) { hs = 0; hphase ^= 1; }
+                    if (++h_cb == prm.cblocks) { h_cb = 0; h_tile += gridDim.x; }
+                };
+                request_halo();
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int n_tile = tile % prm.n_tiles;
+                    for (int cb = 0; cb < prm.cblocks; ++cb) {
+                        request_halo();
+                        const int taps = gm.R * gm.S;
+                        for (int tap = 0; tap < taps; tap += prm.tap_group) {   // weight tiles of tap_group taps: one box
+                            mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 1);
+                            mbar_expect_tx(&full[stage], stage_bytes);
+                            tma_load_3d(smem + (size_t)stage * stage_bytes, &tmap_b, &full[stage], 0, n_tile * BN, cb * taps + tap);
+                            if (++stage == stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+            for (int tile = blockIdx.x; !halo && tile < total_tiles; tile += gridDim.x) {
                 const int n_tile = tile % prm.n_tiles;
                 const int m_tile = tile / prm.n_tiles;
                 const int64_t m0 = (int64_t)m_tile * kBM;
@@ -291,31 +369,73 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            int buf = 0;
-            uint32_t acc_phase = 0;
-            const int n_mma = KC / 32;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
-                tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+        // The issuing thread is latency-bound (one dependent scalar instruction every ~5 cycles), and layers with many
+        // small k-blocks (3x3, C = 64) spent ~650 cycles per k-block here — more than the MMAs themselves (ncu,
+        // profiles/README.md).  So the loop is kept minimal: the whole warp runs it (uniform control flow), descriptors
+        // are 32-bit low words advanced by adds (the high word is loop-invariant), and one lane issues.
+        const uint32_t desc_hi = (prm.sbo16 & 0x3FFFu) | (1u << 14) | ((prm.layout & 7u) << 29);  // SBO, version 1, layout
+        const uint32_t lo_flag = 1u << 16;                                                        // LBO field = 1 (unused)
+        const uint32_t idesc = prm.idesc;
+        const uint32_t base16 = smem_u32(smem) >> 4;            // 16-byte units
+        const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4;
+        const uint32_t xring16 = smem_u32(xring) >> 4, x16 = x_bytes >> 4;
+        const uint32_t wp16 = (uint32_t)(prm.Wp * KC) >> 4, kc16 = (uint32_t)KC >> 4;
+        const int n_mma = KC / 32;
+        const int R = gm.R, S = gm.S, cblocks = prm.cblocks, h_stages = prm.h_stages;
+        int stage = 0, buf = 0, hs = 0;
+        uint32_t phase = 0, acc_phase = 0, hphase = 0;
+        uint32_t stage_lo = base16;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            mbar_wait(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+            uint32_t accumulate = 0;
+            if (halo) {
+                for (int cb = 0; cb < cblocks; ++cb) {
+                    mbar_wait(&xfull[hs], hphase, prm.err_flag, 7);
+                    const uint32_t halo_lo = xring16 + (uint32_t)hs * x16;
+                    const uint32_t b16 = b_bytes >> 4;
+                    int r = 0, s2 = 0;
+                    uint32_t a_lo = halo_lo;   // tap (r, s): the halo rows shifted by r*Wp + s
+                    for (int tap = 0; tap < R * S; tap += prm.tap_group) {
+                        mbar_wait(&full[stage], phase, prm.err_flag, 3);
+                        tc_fence_after();
+                        uint32_t b_lo = stage_lo;
+                        for (int t = 0; t < prm.tap_group; ++t, b_lo += b16) {
+                            if (lane == 0) {
+                                for (int k = 0; k < n_mma; ++k) {  // +32 bytes of K inside the swizzle atom = +2 units
+                                    umma_i8_lohi(tmem_d, (a_lo + 2 * k) | lo_flag, (b_lo + 2 * k) | lo_flag, desc_hi, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                            }
+                            a_lo += kc16;
+                            if (++s2 == S) { s2 = 0; ++r; a_lo = halo_lo + (uint32_t)r * wp16; }
+                        }
+                        if (lane == 0) umma_commit(&empty[stage]);
+                        stage_lo += stage16;
+                        if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
+                    }
+                    if (lane == 0) umma_commit(&xempty[hs]);  // halo slot reusable once every tap's MMAs have read it
+                    if (++hs == h_stages) { hs = 0; hphase ^= 1; }
+                }
+            } else {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[stage], phase, prm.err_flag, 3);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint32_t sb = sa + a_bytes;
-                    const uint64_t adesc = make_smem_desc(sa, prm.sbo16, prm.layout);
-                    const uint64_t bdesc = make_smem_desc(sb, prm.sbo16, prm.layout);
-                    for (int k = 0; k < n_mma; ++k)  // advance 32 bytes of K inside the swizzle atom: +2 in >>4 units
-                        umma_i8(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), prm.idesc, (kb | k) != 0);
-                    umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
-                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                    if (lane == 0) {
+                        for (int k = 0; k < n_mma; ++k) {
+                            umma_i8_lohi(tmem_d, (stage_lo + 2 * k) | lo_flag, (stage_lo + a16 + 2 * k) | lo_flag, desc_hi, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+                    }
+                    stage_lo += stage16;
+                    if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
                 }
-                umma_commit(&acc_full[buf]);  // accumulator complete
-                if (++buf == 2) { buf = 0; acc_phase ^= 1; }
             }
+            if (lane == 0) umma_commit(&acc_full[buf]);  // accumulator complete
+            __syncwarp();
+            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
         }
     } else if (kFQ && warp == 2 + kEpiWarps) {
         // ===================== TMA producer of the fp32 input tiles (fused-quantize variant) =====================
@@ -413,8 +533,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int buf = 0, iter = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-            const int n_tile = tile % prm.n_tiles;
-            const int m_tile = tile / prm.n_tiles;
+            const int m_tile = prm.fd_ntiles.div(tile);
+            const int n_tile = tile - m_tile * prm.n_tiles;
             const int k_base = n_tile * BN;
             // ---- per-tile channel constants (once per CTA when there is a single channel tile) ----
             float* sc = consts + (prm.n_tiles > 1 ? buf : 0) * kConstFloats;
@@ -457,17 +577,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             bool row_ok;
             int img, pq;
             if (kFQ) {  // tiles never straddle images
-                img = m_tile / prm.tiles_per_img;
+                img = prm.fd_tpi.div(m_tile);
                 pq = (m_tile - img * prm.tiles_per_img) * kBM + row;
                 row_ok = pq < PQ;
                 if (!row_ok) pq = 0;
+            } else if (halo) {  // rows are positions of the padded-flat output grid of one image
+                img = prm.fd_tpi.div(m_tile);
+                const int fl = (m_tile - img * prm.tiles_per_img) * kBM + row;
+                const int pp = prm.fd_wp.div(fl), qq = fl - pp * prm.Wp;
+                row_ok = pp < g.P && qq < g.Q;
+                pq = row_ok ? pp * g.Q + qq : 0;
             } else {
                 const int64_t m = (int64_t)m_tile * kBM + row;
                 row_ok = m < prm.M;
-                img = row_ok ? (int)(m / PQ) : 0;
+                img = row_ok ? (prm.M < (1ll << 31) ? prm.fd_pq.div((int)m) : (int)(m / PQ)) : 0;
                 pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
             }
-            const int p = pq / g.Q, q = pq - p * g.Q;
+            const int p = prm.fd_q.div(pq), q = pq - p * g.Q;
             const PixelWindow pw = pixel_window(g, p, q);
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
             // without a class table, a warp with any border pixel computes the window form for all its lanes
@@ -678,6 +804,23 @@ bool umma_supported(const ConvGeom& g) {
     return true;
 }
 
+// Halo variant: stride 1, spatial kernel, the whole halo of a 128-position tile fits one TMA box (<= 256 rows), and
+// the padded-flat tiling does not waste more than ~25 % of the MMA rows (skips 7x7 feature maps).
+bool umma_halo_supported(const ConvGeom& g) {
+    if (!umma_supported(g) || g.stride != 1 || g.R * g.S == 1 || g.C <= 4) return false;
+    const int Wp = g.W + 2 * g.pad;
+    const int halo_rows = kBM + (g.R - 1) * Wp + (g.S - 1);
+    if (halo_rows > 256) return false;
+    const int span = (g.P - 1) * Wp + g.Q;                  // padded-flat positions that hold outputs of one image
+    const int tiles = (span + kBM - 1) / kBM;
+    return g.P * g.Q * 4 >= tiles * kBM * 3;
+}
+
+// Measured (profiles/README.md, A/B per layer): the halo variant wins where k-blocks are small (C = 64: 103 vs 122 us
+// at 56x56) and loses where the weight tiles dominate the L2->SM traffic anyway (C >= 128) or the padded-flat tiling
+// adds a wave (14x14).
+bool umma_halo_profitable(const ConvGeom& g) { return g.Cp == 64 && g.P * g.Q >= 784; }
+
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
     return umma_supported(g) && g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0 && (g.H * g.W) % 4 == 0 &&
            g.C % 64 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
@@ -689,9 +832,11 @@ bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
 bool umma_fused_quant_profitable(const ConvGeom& g) { return g.C == 64 && g.H * g.W >= 784; }
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused) {
+                     cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
     const bool fq = x_fused != nullptr;
+    QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
+               "conv_umma: layer not eligible for the halo variant");
     if (fq) {
         QB_REQUIRE(umma_fused_quant_supported(g, x_fused) && gemm_rows == 0 && aq_fused && aq_fused->qmin && aq_fused->qmax,
                    QB200_EINVAL, "conv_umma: layer not eligible for the fused-quantize kernel");
@@ -719,15 +864,36 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     if (prm.M == 0) return 0;
     prm.KC = fq ? kFqKC : (gm.Cp % 128 == 0) ? 128 : (gm.Cp % 64 == 0) ? 64 : 32;
     prm.cblocks = gm.Cp / prm.KC;
-    prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : 0;
-    prm.m_tiles = fq ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
+    prm.halo = halo ? 1 : 0;
+    prm.Hp = g.H + 2 * g.pad;
+    prm.Wp = g.W + 2 * g.pad;
+    prm.halo_rows = kBM + (g.R - 1) * prm.Wp + (g.S - 1);
+    prm.halo_bytes = (int)align_up_sz((size_t)prm.halo_rows * prm.KC, 1024);
+    prm.h_stages = 0;
+    prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
+    prm.m_tiles = (fq || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
     while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
     prm.BN = BN;
     prm.n_tiles = (g.K + BN - 1) / BN;
-    const size_t stage_bytes = (size_t)(kBM + BN) * prm.KC;
+    prm.fd_ntiles = make_fastdiv(prm.n_tiles);
+    // halo variant: a weight stage holds the tiles of tap_group taps (all taps, one filter row, or one tap — the largest
+    // that still leaves room for 3 stages next to two halo slots); fewer, larger TMA operations keep the single
+    // producer thread off the critical path
+    prm.fd_pq = make_fastdiv(g.P * g.Q);
+    prm.fd_q = make_fastdiv(g.Q);
+    prm.fd_wp = make_fastdiv(prm.Wp);
+    prm.fd_tpi = make_fastdiv(prm.tiles_per_img);
+    prm.tap_group = 1;
+    if (halo) {
+        const size_t b1 = (size_t)BN * prm.KC;
+        const size_t room = kSmemBudget - 1024 - kTailBytes - 2 * (size_t)kMaxWclsBytes - 2 * (size_t)prm.halo_bytes;
+        if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
+        else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
+    }
+    const size_t stage_bytes = halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + BN) * prm.KC;
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
     prm.wcls_smem = 0;
     prm.n_rcls = prm.n_ccls = 0;
@@ -755,7 +921,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         }
     }
     const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (fq ? (size_t)kXStages * kFqKC * kBM * 4 : 0);
-    int stages = (int)((kSmemBudget - 1024 - tail) / stage_bytes);
+    size_t ring_budget = kSmemBudget - 1024 - tail;
+    if (halo) {
+        // halo ring: as many slots (<= 3) as leave at least 4 weight stages
+        int hs = 3;
+        while (hs > 2 && (size_t)hs * prm.halo_bytes + (prm.tap_group > 1 ? 2 : 4) * stage_bytes > ring_budget) --hs;
+        QB_REQUIRE((size_t)hs * prm.halo_bytes + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
+                   "conv_umma: halo tile does not fit shared memory");
+        prm.h_stages = hs;
+        ring_budget -= (size_t)hs * prm.halo_bytes;
+    }
+    int stages = (int)(ring_budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
     prm.stages = stages;
@@ -774,7 +950,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                                  : prm.KC == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
                                                  : CU_TENSOR_MAP_SWIZZLE_32B;
     alignas(64) CUtensorMap tmap_a, tmap_b;
-    if (!fq) {
+    if (halo) {
+        // zero-padded activations as a matrix [N*Hp*Wp rows][Cp bytes]; box = halo_rows x KC; rows past the end are zero
+        cuuint64_t dims[2] = {(cuuint64_t)g.Cp, (cuuint64_t)g.N * prm.Hp * prm.Wp};
+        cuuint64_t strides[1] = {(cuuint64_t)g.Cp};
+        cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)prm.halo_rows};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = api.tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(qa), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(halo) failed with CUresult %d", (int)r);
+    } else if (!fq) {
         // activations: (C, W, H, N) u8, im2col mode; base pixel of an output (p,q) is (q*stride - pad, p*stride - pad)
         cuuint64_t dims[4] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W, (cuuint64_t)gm.H, (cuuint64_t)gm.N};
         cuuint64_t strides[3] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W * gm.Cp, (cuuint64_t)gm.H * gm.W * gm.Cp};
@@ -790,7 +976,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (api.driver_version <= 13010 && (size_t)gm.N * gm.H * gm.W * gm.Cp < 131072)
             reinterpret_cast<uint64_t*>(&tmap_a)[1] &= ~(1ull << 21);
     }
-    {
+    if (halo) {
+        // tap-major weights (KC, K, cblocks*taps); box = KC x BN x tap_group, rows beyond K zero-filled
+        cuuint64_t dims[3] = {(cuuint64_t)prm.KC, (cuuint64_t)g.K, (cuuint64_t)prm.cblocks * g.R * g.S};
+        cuuint64_t strides[2] = {(cuuint64_t)prm.KC, (cuuint64_t)prm.KC * g.K};
+        cuuint32_t box[3] = {(cuuint32_t)prm.KC, (cuuint32_t)BN, (cuuint32_t)prm.tap_group};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = api.tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(wq), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(tap-major weights) failed with CUresult %d", (int)r);
+    } else {
         // weights: [K rows][R*S*Cp bytes], tiled mode, rows beyond K zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)gm.R * gm.S * gm.Cp, (cuuint64_t)g.K};
         cuuint64_t strides[1] = {(cuuint64_t)gm.R * gm.S * gm.Cp};
@@ -802,7 +998,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + tail;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + 1024 /*align*/ + tail;
     static thread_local bool smem_set = false;
     if (!smem_set) {
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));

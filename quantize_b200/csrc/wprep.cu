@@ -25,6 +25,12 @@ PreparedLayout prepared_layout(const qb200_conv_shape& s) {
         L.Kcol = im2col_row_bytes(s.R, s.S);
         L.total = L.wcol_off + align_up_sz((size_t)s.K * L.Kcol, 256);
     }
+    L.tapKC = 0;
+    L.wtap_off = L.total;
+    if (groups == 1 && s.R * s.S > 1 && s.C > 4) {
+        L.tapKC = kblock_bytes(L.Cgp);
+        L.total = L.wtap_off + align_up_sz((size_t)s.K * s.R * s.S * L.Cgp, 256);
+    }
     return L;
 }
 
@@ -79,6 +85,21 @@ __global__ void im2col_weights_kernel(const uint8_t* __restrict__ wq, uint8_t* _
     wcol[i] = v;
 }
 
+// tap-major copy: wtap[((cb*taps + tap)*K + k)*KC + c] = wq[k][tap][cb*KC + c]
+__global__ void tap_major_weights_kernel(const uint8_t* __restrict__ wq, uint8_t* __restrict__ wtap, int K, int taps, int Cgp,
+                                         int KC) {
+    const int64_t total = (int64_t)K * taps * Cgp;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % KC);
+    int64_t t = i / KC;
+    const int k = (int)(t % K);
+    t /= K;
+    const int tap = (int)(t % taps);
+    const int cb = (int)(t / taps);
+    wtap[i] = wq[((int64_t)k * taps + tap) * Cgp + cb * KC + c];
+}
+
 // one warp per output channel
 __global__ void tap_prefix_kernel(const uint8_t* __restrict__ wq, int32_t* __restrict__ wpre, int K, int R, int S,
                                   int Cgp, int is_signed) {
@@ -127,7 +148,8 @@ size_t qb200_conv_prepared_bytes(const qb200_conv_shape* s) {
 size_t qb200_conv_workspace_bytes(const qb200_conv_shape* s) {
     using namespace qb200;
     if (validate_shape(s)) return 0;
-    size_t bytes = (size_t)s->N * s->H * s->W * qb200_padded_channels(s->C);
+    // the larger of: NHWC(Cp), zero-padded NHWC (halo path of stride-1 spatial kernels), im2col rows (few channels)
+    size_t bytes = (size_t)s->N * (s->H + 2 * s->pad) * (s->W + 2 * s->pad) * qb200_padded_channels(s->C);
     if (uses_im2col_rows(*s)) {
         const size_t P = (s->H + 2 * s->pad - s->R) / s->stride + 1, Q = (s->W + 2 * s->pad - s->S) / s->stride + 1;
         const size_t col = (size_t)s->N * P * Q * im2col_row_bytes(s->R, s->S);
@@ -153,6 +175,11 @@ int qb200_conv_prepare_weights(const qb200_conv_shape* s, const uint8_t* w_packe
     QB_LAUNCH_CHECK();
     tap_prefix_kernel<<<s->K, 32, 0, st>>>(wq, wpre, s->K, s->R, s->S, L.Cgp, s->w_sign ? 1 : 0);
     QB_LAUNCH_CHECK();
+    if (L.tapKC) {
+        const int64_t n = (int64_t)s->K * s->R * s->S * L.Cgp;
+        tap_major_weights_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(wq, wq + L.wtap_off, s->K, s->R * s->S, L.Cgp, L.tapKC);
+        QB_LAUNCH_CHECK();
+    }
     if (L.Kcol) {
         im2col_weights_kernel<<<(unsigned)ceil_div64((int64_t)s->K * L.Kcol, 256), 256, 0, st>>>(
             wq, wq + L.wcol_off, s->K, s->C, s->R, s->S, L.Cgp, L.Kcol);

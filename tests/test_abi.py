@@ -43,7 +43,7 @@ def test_pure_host_entry_points(built):
     assert capi.conv_out_hw(s) == (112, 112)         # quantconv2d_float_input.cu:178-179
     s = capi.conv_shape(1, 64, 56, 56, 64, 64, 3, 3, 1, 1, 4, 1)
     assert capi.conv_out_hw(s) == (56, 56)
-    assert L.qb200_conv_workspace_bytes(s) == 56 * 56 * 64
+    assert 56 * 56 * 64 <= L.qb200_conv_workspace_bytes(s) <= 58 * 58 * 64 + 256   # zero-padded NHWC for the halo path
     assert L.qb200_conv_prepared_bytes(s) >= 64 * 9 * 64 + 64 * 16 * 4
     bad = capi.conv_shape(1, 64, 56, 56, 64, 48, 3, 3, 1, 1, 4, 1)
     with pytest.raises(capi.Qb200Error, match="not divisible"):
