@@ -126,13 +126,7 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
                     v[i] = (c0 + i < C) ? ldg_stream4(xp + (int64_t)i * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             uint32_t w[4][4];  // [pixel][word]
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                w[0][k] = quant_word(v[4 * k].x, v[4 * k + 1].x, v[4 * k + 2].x, v[4 * k + 3].x, p);
-                w[1][k] = quant_word(v[4 * k].y, v[4 * k + 1].y, v[4 * k + 2].y, v[4 * k + 3].y, p);
-                w[2][k] = quant_word(v[4 * k].z, v[4 * k + 1].z, v[4 * k + 2].z, v[4 * k + 3].z, p);
-                w[3][k] = quant_word(v[4 * k].w, v[4 * k + 1].w, v[4 * k + 2].w, v[4 * k + 3].w, p);
-            }
+            quant_tile<4>(v, w, p);
             // padded channels must be exactly 0 even when qmin > 0
             if (c0 + 16 > C) {
 #pragma unroll

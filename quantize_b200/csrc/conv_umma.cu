@@ -33,10 +33,10 @@ constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each ow
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kFqWarps = 8;         // fused-quantize variant: quantizer warps, each owns 8 channels x 128 pixels of a k-block
 constexpr int kThreadsFq = kThreads + 32 + kFqWarps * 32;  // + one TMA warp for the fp32 tiles
-constexpr int kXStages = 3;         // fp32 staging ring of the fused-quantize variant
+constexpr int kMaxXStages = 6;      // fp32 staging ring of the fused-quantize variant (3..6 slots, what fits) / halo ring (<= 3)
 constexpr int kFqKC = 64;           // its k-block: 64 channels (a 32 KB fp32 tile, an 8 KB u8 A tile)
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
-constexpr int kBarBytes = 512;                           // mbarriers + TMEM slot
+constexpr int kBarBytes = 576;                           // mbarriers + TMEM slot
 constexpr int kTailBytes = kBarBytes + 2 * kConstFloats * 4;  // barriers + two constant buffers
 constexpr int kMaxWclsBytes = 16 * 1024;                 // one buffer of per-window-class channel sums (layers with R*S > 1)
 constexpr int kMaxCls = 16;                              // distinct row (and column) windows supported by the class table
@@ -44,6 +44,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
 constexpr int kMaxStages = 24;      // small stages (weight-only tiles of the halo variant) need depth to cover TMA latency
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemBudgetFq = 224 * 1024;  // the fused-quantize variant wants every byte for fp32 tiles in flight
 
 // Division of a non-negative 32-bit value by a launch-time constant as one multiply-high + shift: the per-tile index
 // arithmetic of the epilogue (tile -> image, row, column) otherwise costs ~40 instructions per division.
@@ -93,6 +94,7 @@ struct UmmaParams {
     // (tests/native/desc_shift.cu shows the hardware swizzles on absolute addresses, so shifted descriptors are exact).
     int halo;          // 0/1
     int Hp, Wp, halo_rows, halo_bytes, h_stages;
+    int x_stages;  // fused-quantize variant: slots of the fp32 ring
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
     int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
     const float* x;
@@ -129,12 +131,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Polling wait with a plain timed sleep between polls (no barrier-armed suspend): for warps that wait for a long time
+// next to instruction-bound warps.  Measured: after a try_wait suspend has been cut short once, the re-armed suspends of
+// the same wait return at once and the loop spins (8 M iterations on one layer), stealing issue slots.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+template <int kSleepNs>
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        __nanosleep(kSleepNs);
+        if ((++spins & 0xFFu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 8000000000ll) {
+                if (err_flag) atomicExch(err_flag, code);
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+}
 // Bounded wait: a lost arrival must not hang the GPU — after ~4 s the kernel flags the error and traps.
+// kSleepNs > 0: back off between polls (latency-insensitive waiters that share an SM with instruction-bound warps).
+template <int kSleepNs = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
     long long t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if (kSleepNs > 0) __nanosleep(kSleepNs);
         if ((++spins & 0xFFu) == 0) {  // look at the clock only every 256 wake-ups
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -261,17 +297,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool halo = !kFQ && prm.halo != 0;
     const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = BN * KC,
                    stage_bytes = halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes;
-    uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [kXStages][KC][128] fp32
+    uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [x_stages][KC][128] fp32
     const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u);  // ring slot size
-    const int x_slots = kFQ ? kXStages : (halo ? prm.h_stages : 0);       // fp32 tiles (kFQ) or u8 halo tiles (halo)
+    const int x_slots = kFQ ? prm.x_stages : (halo ? prm.h_stages : 0);       // fp32 tiles (kFQ) or u8 halo tiles (halo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)x_slots * x_bytes);
     uint64_t* full = bars;                     // [stages]
     uint64_t* empty = bars + kMaxStages;       // [stages]
     uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
     uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
-    uint64_t* xfull = bars + 2 * kMaxStages + 4;     // [kXStages]
-    uint64_t* xempty = xfull + kXStages;             // [kXStages]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kXStages);
+    uint64_t* xfull = bars + 2 * kMaxStages + 4;     // [kMaxXStages]
+    uint64_t* xempty = xfull + kMaxXStages;          // [kMaxXStages]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kMaxXStages);
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][3][256]
     float* wcls_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][n_cls][BN]
 
@@ -284,16 +320,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int i = 0; i < stages; ++i) {
-            mbar_init(&full[i], kFQ ? 1 + kFqWarps * 32 : 1);  // TMA expect_tx arrival (+ every quantizer thread)
+            mbar_init(&full[i], kFQ ? 1 + kFqWarps : 1);  // TMA expect_tx arrival (+ one arrival per quantizer warp)
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], kEpiWarps);
         }
-        for (int i = 0; i < kXStages; ++i) {
+        for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&xfull[i], 1);
-            mbar_init(&xempty[i], kFQ ? kFqWarps * 32 : 1);
+            mbar_init(&xempty[i], kFQ ? kFqWarps : 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -353,7 +389,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int r = 0; r < gm.R; ++r)
                     for (int s = 0; s < gm.S; ++s)
                         for (int cb = 0; cb < prm.cblocks; ++cb) {
-                            mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 1);
+                            mbar_wait<kFQ ? 200 : 0>(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
                             if (kFQ) {
@@ -386,7 +422,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t phase = 0, acc_phase = 0, hphase = 0;
         uint32_t stage_lo = base16;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
+            mbar_wait<kFQ ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
             uint32_t accumulate = 0;
@@ -420,7 +456,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             } else {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait(&full[stage], phase, prm.err_flag, 3);
+                    mbar_wait<kFQ ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
                     tc_fence_after();
                     if (lane == 0) {
                         for (int k = 0; k < n_mma; ++k) {
@@ -440,7 +476,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     } else if (kFQ && warp == 2 + kEpiWarps) {
         // ===================== TMA producer of the fp32 input tiles (fused-quantize variant) =====================
         if (lane == 0) {
-            // The shared-memory ring holds only kXStages tiles; HBM latency is covered by prefetching the tiles of the
+            // The shared-memory ring holds only x_stages tiles; HBM latency is covered by prefetching the tiles of the
             // next kPrefetch k-blocks into L2 (the ring loads then hit L2).
             constexpr int kPrefetch = 0;   // measured: prefetching 10 k-blocks ahead thrashes L2 (1.7x DRAM reads); the ring alone is better
             int pf_tile = blockIdx.x, pf_cb = 0;
@@ -452,18 +488,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (++pf_cb == prm.cblocks) { pf_cb = 0; pf_tile += gridDim.x; }
             };
             for (int i = 0; i < kPrefetch; ++i) prefetch_next();
-            uint32_t kbg = 0;
+            int xs = 0;
+            uint32_t xphase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m_tile = tile / prm.n_tiles;
                 const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
-                for (int cb = 0; cb < prm.cblocks; ++cb, ++kbg) {
+                for (int cb = 0; cb < prm.cblocks; ++cb) {
                     prefetch_next();
-                    const int xs = (int)(kbg % kXStages);
-                    const uint32_t xphase = (kbg / kXStages) & 1u;
-                    mbar_wait(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
+                    mbar_wait<200>(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
                     mbar_expect_tx(&xfull[xs], x_bytes);
                     // box [128 pixels][KC channels] of image img; pixels beyond H*W are zero-filled
                     tma_load_3d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], t * kBM, cb * KC, img);
+                    if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
                 }
             }
         }
@@ -479,43 +515,54 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int j16 = pw >> 1;          // 16-byte channel chunk of the A row this warp contributes to
         const int half = pw & 1;          // which 8 bytes of that chunk
         const int rot = lane >> 1;
-        uint32_t kbg = 0;
+        int xs = 0, stage = 0;
+        uint32_t xphase = 0, phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            for (int cb = 0; cb < prm.cblocks; ++cb, ++kbg) {
-                const int xs = (int)(kbg % kXStages);
-                const uint32_t xphase = (kbg / kXStages) & 1u;
-                const int stage = (int)(kbg % (uint32_t)stages);
-                const uint32_t phase = (kbg / (uint32_t)stages) & 1u;
+            for (int cb = 0; cb < prm.cblocks; ++cb) {
                 mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
                 const float4* xt = reinterpret_cast<const float4*>(xring + (size_t)xs * x_bytes) + (pw * 8) * (kBM / 4) + lane;
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = xt[i * (kBM / 4)];
                 uint32_t w[4][2];  // [pixel][word]
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    w[0][k] = quant_word(v[4 * k].x, v[4 * k + 1].x, v[4 * k + 2].x, v[4 * k + 3].x, qp);
-                    w[1][k] = quant_word(v[4 * k].y, v[4 * k + 1].y, v[4 * k + 2].y, v[4 * k + 3].y, qp);
-                    w[2][k] = quant_word(v[4 * k].z, v[4 * k + 1].z, v[4 * k + 2].z, v[4 * k + 3].z, qp);
-                    w[3][k] = quant_word(v[4 * k].w, v[4 * k + 1].w, v[4 * k + 2].w, v[4 * k + 3].w, qp);
-                }
-                mbar_arrive(&xempty[xs]);  // this thread's part of the fp32 tile is in registers
+                quant_tile<2>(v, w, qp);
+                // One arrival per WARP (after a warp sync), not per thread: every mbarrier arrival wakes the warps that
+                // sleep on any barrier of the CTA, and 512 arrivals per k-block kept the idle epilogue warps spinning
+                // through a third of the issue slots (ncu: 14.6 M NANOSLEEP wake-ups on one layer).
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xempty[xs]);  // this warp's part of the fp32 tile is in registers
                 mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
                 uint8_t* sa = smem + (size_t)stage * stage_bytes;
                 // lanes rotate which of their 4 pixels they store in each step so that one store instruction spreads
-                // over all swizzle phases; SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+                // over all swizzle phases; SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3.  The rotation is applied
+                // to the registers with selects (a dynamic register index compiles to a branchy loop that cost a third
+                // of the quantizer's time), after which step t stores w[t] to pixel (t + rot) & 3.
+                if (rot & 1) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t t0 = w[0][k];
+                        w[0][k] = w[1][k]; w[1][k] = w[2][k]; w[2][k] = w[3][k]; w[3][k] = t0;
+                    }
+                }
+                if (rot & 2) {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t t0 = w[0][k], t1 = w[1][k];
+                        w[0][k] = w[2][k]; w[1][k] = w[3][k]; w[2][k] = t0; w[3][k] = t1;
+                    }
+                }
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     const int px = (t + rot) & 3;
-                    uint2 val;
-                    val.x = px == 0 ? w[0][0] : px == 1 ? w[1][0] : px == 2 ? w[2][0] : w[3][0];
-                    val.y = px == 0 ? w[0][1] : px == 1 ? w[1][1] : px == 2 ? w[2][1] : w[3][1];
                     const int row = lane * 4 + px;
                     const int jj = j16 ^ ((row >> 1) & 3);
-                    *reinterpret_cast<uint2*>(sa + row * kFqKC + (jj << 4) + (half << 3)) = val;
+                    *reinterpret_cast<uint2*>(sa + row * kFqKC + (jj << 4) + (half << 3)) = make_uint2(w[t][0], w[t][1]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
-                mbar_arrive(&full[stage]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
     } else {
@@ -614,7 +661,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int i11 = pw.r1 * s1 + pw.s1, i01 = pw.r0 * s1 + pw.s1, i10 = pw.r1 * s1 + pw.s0, i00 = pw.r0 * s1 + pw.s0;
             const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
 
-            mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
+            if (kFQ) mbar_wait_sleepy<500>(&acc_full[buf], acc_phase, prm.err_flag, 4);
+            else mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride + half * cols);
             for (int c0 = 0; c0 < cols; c0 += 32) {
@@ -829,7 +877,11 @@ bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
 // Measured on B200 (profiles/README.md): the in-kernel quantizer (8 warps) sustains ~3.5 TB/s of fp32 input, the
 // standalone quantizer ~5.5 TB/s.  Fusing wins when the layer is output-heavy and large: one 64-channel k-block per
 // tile (C == 64) on feature maps of at least 28x28; everything else keeps the two-kernel path.
-bool umma_fused_quant_profitable(const ConvGeom& g) { return g.C == 64 && g.H * g.W >= 784; }
+// Measured on ResNet-50's 1x1 layers at batch 256 (profiles/README.md): fusing wins when the layer is input-heavy (a
+// single 64-channel k-block, or at least twice as many input as output channels) and each image has >= 7 tiles; layers
+// with several channel tiles would quantize the same pixels once per channel tile, and 14x14 / 7x7 layers are ring-
+// latency bound, so those keep the standalone quantizer.
+bool umma_fused_quant_profitable(const ConvGeom& g) { return g.H * g.W >= 784 && (g.C == 64 || g.C >= 2 * g.K); }
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo) {
@@ -870,6 +922,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.halo_rows = kBM + (g.R - 1) * prm.Wp + (g.S - 1);
     prm.halo_bytes = (int)align_up_sz((size_t)prm.halo_rows * prm.KC, 1024);
     prm.h_stages = 0;
+    prm.x_stages = 0;
     prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
     prm.m_tiles = (fq || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
@@ -920,8 +973,18 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             prm.wcls_smem = nr * nc * BN * 4;
         }
     }
-    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (fq ? (size_t)kXStages * kFqKC * kBM * 4 : 0);
-    size_t ring_budget = kSmemBudget - 1024 - tail;
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem;
+    size_t ring_budget = (fq ? kSmemBudgetFq : kSmemBudget) - 1024 - tail;
+    const size_t xb = (size_t)kFqKC * kBM * 4;
+    if (fq) {
+        // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
+        int xs = kMaxXStages;
+        while (xs > 3 && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
+        QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
+                   "conv_umma: fused-quantize tile does not fit shared memory");
+        prm.x_stages = xs;
+        ring_budget -= (size_t)xs * xb;
+    }
     if (halo) {
         // halo ring: as many slots (<= 3) as leave at least 4 weight stages
         int hs = 3;
@@ -998,11 +1061,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + 1024 /*align*/ + tail;
+    const size_t smem = (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + (fq ? prm.x_stages * xb : 0) +
+                        1024 /*align*/ + tail;
     static thread_local bool smem_set = false;
     if (!smem_set) {
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         smem_set = true;
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
