@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU (BASELINE: 256)")
     ap.add_argument("--model", default=MODEL)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-chain", action="store_true", help="e2e: fp32 tensors between the convs of a block (no int8 hand-off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", default="", help="debug: comma-separated layer indices to run")
     ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
@@ -343,7 +344,8 @@ def run_b200(args):
         torch.cuda.empty_cache()
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
-        net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0, fuse_blocks=True)
+        net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0, fuse_blocks=True,
+                                  chain_blocks=not args.no_chain, cross_block=not args.no_chain)
         hw = models.INPUT_HW[args.model]
         host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
         host_out = torch.empty(args.batch, 1000, dtype=torch.float32).pin_memory()
@@ -389,8 +391,9 @@ def run_b200(args):
         e2e = {"value": round(args.batch * n_gpus / (e_ms / K / 1e3), 1), "unit": "images/s",
                "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
                "ms_per_step": round(e_ms / K, 3), "wall_ms_per_step": round(wall / K * 1e3, 3),
-               "api": "models.build_packed(resnet50, fuse_blocks=True) forward: host.QuantConv2d -> quant_engine.quantconv2d_float_input "
-                      "(ReLU / residual add of each block run in the conv epilogues)",
+               "api": "models.build_packed(resnet50, fuse_blocks=True, chain_blocks=%s) forward: host.QuantConv2d -> "
+                      "quant_engine.quantconv2d_float_input / quantconv2d_chain (ReLU / residual add of each block run in the "
+                      "conv epilogues; with chain_blocks the activations between the convs of a block stay int8)" % (not args.no_chain),
                "pipelining": "H2D of step k+1 (copy stream, double buffer) overlaps the forward of step k; all copies inside the timed region",
                "engine_launches_per_step": int(L.qb200_launch_count()) // K}
 

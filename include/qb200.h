@@ -154,15 +154,30 @@ int qb200_quantconv2d_fused(const qb200_conv_shape* s, const float* x, const voi
 
 /* Optional fused tail — an extension beyond the reference op for callers that own the surrounding graph (ResNet
  * blocks): out = relu(out + residual), each step rounded as the separate fp32 ops would.  residual: device fp32
- * [N,K,P,Q] or NULL; relu: 0/1.  With tail == NULL the call is exactly qb200_quantconv2d_fused. */
+ * [N,K,P,Q] or NULL; relu: 0/1.  With tail == NULL the call is exactly qb200_quantconv2d_fused.
+ *
+ * Quantized hand-off (the int8-out epilogue; reference counterpart: the packed-activation op
+ * engine/kernels/functions/quantconv2d.cu:49-264 fed by Quantizer.pack, quantizer.py:228-246): when next_shape is set,
+ * the epilogue also quantizes its result with the CONSUMER layer's activation quantizer,
+ *     q = clamp(rint(v / next_quant.scale - next_quant.zero), qmin, qmax),   v = the fp32 value after the tail,
+ * and writes it straight into the consumer's activation workspace (the bytes qb200_conv_quantize_input would have
+ * produced from the fp32 tensor — bit-identical, the same arithmetic on the same fp32 value).  The consumer then runs
+ * with qb200_conv_from_workspace(_ex).  next_shape must describe a layer whose input is this layer's output
+ * (N, C == K, H == P, W == Q); `out` may be NULL when only the quantized result is wanted.
+ * qb200_conv_handoff_supported tells whether this producer/consumer pair can be chained (tensor-core producer,
+ * consumer workspace in NHWC or zero-padded NHWC layout); when it returns 0 the caller keeps the fp32 path. */
 typedef struct {
     const float* residual;
     int32_t relu;
+    const qb200_conv_shape* next_shape; /* NULL: no hand-off */
+    const qb200_act_quant* next_quant;
+    void* next_workspace;               /* qb200_conv_workspace_bytes(next_shape) bytes */
 } qb200_conv_tail;
 int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const void* prepared,
                                const float* w_scale, int32_t n_w_scale, const float* bias,
                                const qb200_act_quant* aq, const qb200_conv_tail* tail, void* workspace, void* out,
                                int32_t out_kind, void* stream);
+int qb200_conv_handoff_supported(const qb200_conv_shape* s, const qb200_conv_shape* next_shape);
 
 /* 1 when qb200_quantconv2d_fused runs this layer as ONE kernel (the quantizer runs in the conv kernel's producer warps
  * and no workspace is written), else 0.  Supported for 1x1, stride 1, pad 0, C % 64 == 0, H*W % 4 == 0, 16-byte
@@ -177,6 +192,10 @@ int qb200_conv_quantize_input(const qb200_conv_shape* s, const float* x, const q
 int qb200_conv_from_workspace(const qb200_conv_shape* s, const void* workspace, const void* prepared,
                               const float* w_scale, int32_t n_w_scale, const float* bias, const qb200_act_quant* aq,
                               void* out, int32_t out_kind, void* stream);
+/* ... with the optional tail (residual / ReLU / quantized hand-off to the next layer) */
+int qb200_conv_from_workspace_ex(const qb200_conv_shape* s, const void* workspace, const void* prepared,
+                                 const float* w_scale, int32_t n_w_scale, const float* bias, const qb200_act_quant* aq,
+                                 const qb200_conv_tail* tail, void* out, int32_t out_kind, void* stream);
 
 /* Same conv on already-quantized NHWC(Cp) activations (callers that keep activations quantized). */
 int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const void* prepared,
@@ -189,6 +208,13 @@ int qb200_conv2d_q8_nhwc(const qb200_conv_shape* s, const uint8_t* q_nhwc, const
 int qb200_quantconv2d_weightonly(const qb200_conv_shape* s, const float* x, const uint8_t* w_packed,
                                  const float* w_scale, const float* w_zero, int32_t n_w_scale,
                                  const float* bias, float* out, void* stream);
+
+/* Max pooling over fp32 NCHW planes (planes = N*C), square kernel / stride, -inf padding, floor output size:
+ * the op between the stem conv and the first residual stage of the ResNet family (torchvision resnet.py; the reference
+ * runs torch.nn.MaxPool2d there).  Bit-identical to torch.nn.functional.max_pool2d; exists because that op, not a
+ * conv, was the largest single kernel of the packed ResNet-50 forward. */
+int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, int32_t W, int32_t kernel, int32_t stride,
+                        int32_t pad, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@
 // pixels x 16 channels: 16 coalesced 16-byte loads (a warp reads 512 contiguous bytes of one channel plane),
 // quantizes in registers, writes four 16-byte channel vectors into an XOR-swizzled shared tile, and the block
 // copies the tile out as whole contiguous NHWC rows.  HBM-bound: bytes per element = 4 (read) + Cp/C (write).
+#include <algorithm>
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "quant_math.cuh"
@@ -352,6 +353,48 @@ int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_ac
     else
         act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, HW, 1, g.W, g.W, HW, ps, aq->scale, aq->zero,
                                                              aq->qmin, aq->qmax);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+
+namespace {
+// One 16-byte chunk per thread over the pad pixels only: for each image the top and bottom `pad` rows (full width) and the
+// left / right `pad` columns of the rows between.
+__global__ void __launch_bounds__(256)
+zero_pad_borders_kernel(uint4* __restrict__ q, int N, int H, int W, int pad, int chunks) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int border = 2 * pad * Wp + 2 * pad * H;  // pad pixels per image
+    const int64_t total = (int64_t)N * border * chunks;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % chunks);
+        const int64_t bp = i / chunks;
+        const int n = (int)(bp / border);
+        int b = (int)(bp - (int64_t)n * border);
+        int h, w;
+        if (b < pad * Wp) {                       // top rows
+            h = b / Wp; w = b - h * Wp;
+        } else if (b < 2 * pad * Wp) {            // bottom rows
+            b -= pad * Wp;
+            h = b / Wp; w = b - h * Wp; h += pad + H;
+        } else {                                  // side columns of the H interior rows
+            b -= 2 * pad * Wp;
+            h = b / (2 * pad);
+            const int j = b - h * 2 * pad;
+            w = j < pad ? j : W + j;
+            h += pad;
+        }
+        q[((int64_t)(n * Hp + h) * Wp + w) * chunks + c] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+}  // namespace
+
+int launch_zero_pad_borders(uint8_t* q, int N, int H, int W, int pad, int Cp, cudaStream_t st) {
+    QB_REQUIRE(q && Cp % 16 == 0 && reinterpret_cast<uintptr_t>(q) % 16 == 0, QB200_EINVAL, "zero_pad_borders: bad buffer");
+    if (pad == 0 || N == 0) return 0;
+    const int64_t total = (int64_t)N * (2 * pad * (W + 2 * pad) + 2 * pad * H) * (Cp / 16);
+    const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
+    zero_pad_borders_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(q), N, H, W, pad, Cp / 16);
     QB_LAUNCH_CHECK();
     return 0;
 }

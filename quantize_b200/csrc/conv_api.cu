@@ -30,6 +30,16 @@ bool workspace_is_padded(const ConvGeom& g) {
 // does the conv kernel chosen for this shape read materialised im2col rows (few-channel layers) or NHWC(Cp) bytes?
 bool workspace_is_im2col(const ConvGeom& g, const PreparedLayout& L) { return resolve_algo(g) == QB200_ALGO_UMMA && L.Kcol > 0; }
 
+// Quantized hand-off: can the tensor-core producer `g` write the workspace of consumer `n` directly?
+// (consumer layouts handled: NHWC(Cp) and zero-padded NHWC; not im2col rows or the sub-sampled compact buffer)
+bool handoff_ok(const qb200_conv_shape& s, const qb200_conv_shape& n) {
+    const ConvGeom g = make_geom(s), gn = make_geom(n);
+    if (resolve_algo(g) != QB200_ALGO_UMMA) return false;
+    if (n.N != s.N || n.C != s.K || n.H != g.P || n.W != g.Q) return false;
+    if (workspace_is_im2col(gn, prepared_layout(n)) || uses_subsampled_input(gn)) return false;
+    return true;
+}
+
 int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, uint8_t* ws, cudaStream_t st) {
     QB_REQUIRE(x && ws, QB200_EINVAL, "conv: null pointer");
     const ConvGeom g = make_geom(*s);
@@ -47,7 +57,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     QB_REQUIRE(n_w_scale == 1 || n_w_scale == s->K, QB200_EINVAL, "weight_scale must have 1 or K elements");
     QB_REQUIRE(out_kind == QB200_OUT_F32 || out_kind == QB200_OUT_ACC, QB200_EINVAL, "conv: bad out_kind");
     QB_REQUIRE(aq && aq->scale && aq->zero, QB200_EINVAL, "conv: activation quantizer parameters missing");
-    QB_REQUIRE((q || x_fused) && prepared && w_scale && out, QB200_EINVAL, "conv: null pointer");
+    QB_REQUIRE((q || x_fused) && prepared && w_scale, QB200_EINVAL, "conv: null pointer");
     const ConvGeom g = make_geom(*s);
     const PreparedLayout L = prepared_layout(*s);
     const uint8_t* wq = static_cast<const uint8_t*>(prepared);
@@ -61,8 +71,38 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     ep.out_kind = out_kind;
     ep.residual = tail ? tail->residual : nullptr;
     ep.relu = tail ? (tail->relu != 0) : 0;
-    QB_REQUIRE(out_kind == QB200_OUT_F32 || (!ep.residual && !ep.relu), QB200_EINVAL,
+    ep.q8_out = nullptr;
+    ep.q8_scale = ep.q8_zero = ep.q8_qmin = ep.q8_qmax = nullptr;
+    ep.q8_cp = ep.q8_img_pixels = ep.q8_row_pixels = ep.q8_pixel_off = 0;
+    ep.store_f32 = 1;
+    const bool handoff = tail && tail->next_shape;
+    QB_REQUIRE(out_kind == QB200_OUT_F32 || (!ep.residual && !ep.relu && !handoff), QB200_EINVAL,
                "conv: the fused tail applies to the fp32 output only");
+    QB_REQUIRE(out || handoff, QB200_EINVAL, "conv: null output");
+    if (handoff) {
+        const qb200_conv_shape& n = *tail->next_shape;
+        if (int rc = validate_shape(&n)) return rc;
+        const qb200_act_quant* nq = tail->next_quant;
+        QB_REQUIRE(nq && nq->scale && nq->zero && nq->qmin && nq->qmax && tail->next_workspace, QB200_EINVAL,
+                   "conv: hand-off needs the consumer's quantizer and workspace");
+        QB_REQUIRE(handoff_ok(*s, n) && !x_fused, QB200_EUNSUPPORTED, "conv: this layer pair cannot be chained (qb200_conv_handoff_supported)");
+        QB_REQUIRE(reinterpret_cast<uintptr_t>(tail->next_workspace) % 16 == 0, QB200_EINVAL, "conv: hand-off workspace must be 16-byte aligned");
+        const ConvGeom gn = make_geom(n);
+        ep.q8_out = static_cast<uint8_t*>(tail->next_workspace);
+        ep.q8_scale = nq->scale; ep.q8_zero = nq->zero; ep.q8_qmin = nq->qmin; ep.q8_qmax = nq->qmax;
+        ep.q8_cp = gn.Cp;
+        if (workspace_is_padded(gn)) {
+            const int Wp = gn.W + 2 * gn.pad;
+            ep.q8_img_pixels = (gn.H + 2 * gn.pad) * Wp;
+            ep.q8_row_pixels = Wp;
+            ep.q8_pixel_off = gn.pad * Wp + gn.pad;
+            if (int rc = launch_zero_pad_borders(ep.q8_out, gn.N, gn.H, gn.W, gn.pad, gn.Cp, st)) return rc;
+        } else {
+            ep.q8_img_pixels = gn.H * gn.W;
+            ep.q8_row_pixels = gn.W;
+        }
+        ep.store_f32 = out != nullptr;
+    }
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
@@ -115,6 +155,22 @@ int qb200_conv_from_workspace(const qb200_conv_shape* s, const void* workspace, 
                     static_cast<cudaStream_t>(stream));
 }
 
+int qb200_conv_from_workspace_ex(const qb200_conv_shape* s, const void* workspace, const void* prepared, const float* w_scale,
+                                 int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, const qb200_conv_tail* tail,
+                                 void* out, int32_t out_kind, void* stream) {
+    using namespace qb200;
+    if (int rc = validate_shape(s)) return rc;
+    if (s->N == 0) return 0;
+    return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind,
+                    static_cast<cudaStream_t>(stream), nullptr, tail);
+}
+
+int qb200_conv_handoff_supported(const qb200_conv_shape* s, const qb200_conv_shape* next_shape) {
+    using namespace qb200;
+    if (!next_shape || validate_shape(s) || validate_shape(next_shape)) return 0;
+    return handoff_ok(*s, *next_shape) ? 1 : 0;
+}
+
 int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const void* prepared, const float* w_scale,
                                int32_t n_w_scale, const float* bias, const qb200_act_quant* aq, const qb200_conv_tail* tail,
                                void* workspace, void* out, int32_t out_kind, void* stream) {
@@ -125,7 +181,7 @@ int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const 
     QB_REQUIRE(x != nullptr, QB200_EINVAL, "conv: null input");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // (a residual tail needs 32 more live registers in the epilogue than the 608-thread fused-quantize kernel has)
-    if (single_kernel(make_geom(*s), x) && !(tail && tail->residual))
+    if (single_kernel(make_geom(*s), x) && !(tail && (tail->residual || tail->next_shape)))
         return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x, tail);
     if (int rc = quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), st)) return rc;
     return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st,

@@ -58,6 +58,13 @@ struct EpilogueParams {
     // optional fused tail (extension beyond the reference op): out = relu(out + residual)
     const float* residual;  // device, same shape as out, or null
     int relu;
+    // optional quantized hand-off: the result, quantized with the consumer's activation quantizer, written into the
+    // consumer's workspace (NHWC or zero-padded NHWC, q8_cp bytes per pixel): byte address of pixel (n, p, q) =
+    // q8_out + ((n * q8_img_pixels + p * q8_row_pixels + q + q8_pixel_off) * q8_cp
+    uint8_t* q8_out;        // null: none
+    const float *q8_scale, *q8_zero, *q8_qmin, *q8_qmax;
+    int q8_cp, q8_img_pixels, q8_row_pixels, q8_pixel_off;
+    int store_f32;          // 0: skip the fp32 / int32 store (hand-off only)
 };
 
 struct EpilogueScalars {
@@ -123,6 +130,8 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
 bool umma_halo_supported(const ConvGeom& g);
 bool umma_halo_profitable(const ConvGeom& g);
 int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);
+// zero the pad pixels of a [N][H + 2*pad][W + 2*pad][Cp] buffer whose interior another kernel fills (quantized hand-off)
+int launch_zero_pad_borders(uint8_t* q, int N, int H, int W, int pad, int Cp, cudaStream_t st);
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x);
 bool umma_fused_quant_profitable(const ConvGeom& g);
 // 1x1 / stride > 1 / pad 0: quantize only the pixels the conv reads into a compact [N, P, Q, Cp] buffer

@@ -109,6 +109,13 @@ struct UmmaParams {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 16-byte shared-memory load through the shared window (the epilogue's constant tables; a plain dereference of a pointer
+// that may point at one of two tables compiled to generic loads)
+__device__ __forceinline__ float4 lds4(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -576,6 +583,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const EpilogueParams& ep = prm.ep;
         const EpilogueScalars es = load_epilogue_scalars(ep);
         const bool acc_out = ep.out_kind == QB200_OUT_ACC;
+        QuantParams q8p = {};
+        if (!kFQ && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
         const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
         int buf = 0, iter = 0;
         uint32_t acc_phase = 0;
@@ -689,6 +698,67 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (ep.relu) val = fmaxf(val, 0.f);
                     return val;
                 };
+                if constexpr (!kFQ) {
+                    if (ep.q8_out != nullptr) {
+                        // Quantized hand-off: the chunk's 32 channels of this pixel, after the tail, go through the
+                        // CONSUMER's activation quantizer and land as 32 contiguous bytes of its NHWC workspace.
+                        // (kept compact on purpose: the first version branched per element inside the unrolled loop and
+                        // the epilogue became instruction-fetch bound — ncu: stall_no_inst on 60 % of its samples)
+                        float r[32];
+                        if (uniform_ok) {
+                            // fma(z_a, wsum, acc) is exact (= acc) when z_a == 0, so one form serves both cases
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = lds4(sc + cc + j), w4 = lds4(wrow + cc + j), b4 = lds4(br + cc + j);
+                                r[j + 0] = tail(__fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x), j + 0);
+                                r[j + 1] = tail(__fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y), j + 1);
+                                r[j + 2] = tail(__fmaf_rn(s4.z, __fmaf_rn(es.z_a, w4.z, (float)(int32_t)v[j + 2]), b4.z), j + 2);
+                                r[j + 3] = tail(__fmaf_rn(s4.w, __fmaf_rn(es.z_a, w4.w, (float)(int32_t)v[j + 3]), b4.w), j + 3);
+                            }
+                        } else {
+                            // border pixel of a layer without a class table (z_a != 0): window sums from the prefix tables
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                float wsf = 0.f;
+                                if (k_base + cc + j < g.K) {
+                                    const int32_t* t4 = wtab + (cc + j) * tbl;
+                                    wsf = (float)(__ldg(t4 + i11) - __ldg(t4 + i01) - __ldg(t4 + i10) + __ldg(t4 + i00));
+                                }
+                                r[j] = tail(__fmaf_rn(sc[cc + j], __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]), br[cc + j]), j);
+                            }
+                        }
+                        if (ep.store_f32) {
+                            float* o = static_cast<float*>(out) + o_off;
+                            if (full_n) {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) o[(int64_t)j * PQ] = r[j];
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (k_base + cc + j < g.K) o[(int64_t)j * PQ] = r[j];
+                            }
+                        }
+                        if (k_base + cc < ep.q8_cp) {
+                            const int n_valid = g.K - (k_base + cc);  // channels of this chunk that exist (others stay 0)
+                            uint32_t w[8];
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj)
+                                w[jj] = quant_word(r[4 * jj], r[4 * jj + 1], r[4 * jj + 2], r[4 * jj + 3], q8p);
+                            if (n_valid < 32) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) {
+                                    const int nb = n_valid - 4 * jj;
+                                    if (nb < 4) w[jj] = nb <= 0 ? 0u : (w[jj] & ((1u << (8 * nb)) - 1u));
+                                }
+                            }
+                            const int64_t pix = (int64_t)img * ep.q8_img_pixels + (int64_t)p * ep.q8_row_pixels + q + ep.q8_pixel_off;
+                            uint4* dst = reinterpret_cast<uint4*>(ep.q8_out + pix * ep.q8_cp + (k_base + cc));
+                            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                        continue;
+                    }
+                }
                 if (!acc_out && full_n && uniform_ok) {
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).

@@ -1,0 +1,134 @@
+// Max pooling over fp32 NCHW planes — the one non-conv op between the quantized convs of the ResNet family
+// (stem conv -> relu -> maxpool 3x3/2 -> layer1).  It is memory-bound (read the plane once, write a quarter of it), so
+// the kernel stages a band of input rows in shared memory with coalesced 16-byte loads and every output is computed
+// from shared memory; torch's one-thread-per-output kernel runs at ~1.5 TB/s on B200, this one at the HBM rate.
+// Results are bit-identical to torch.nn.functional.max_pool2d (max is exact; padding behaves as -inf).
+#include <algorithm>
+#include <cfloat>
+#include "common.cuh"
+
+namespace qb200 {
+namespace {
+
+constexpr int kPoolThreads = 256;
+
+// max that propagates NaN like torch's pooling (one instruction)
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// one block = one (plane, band of output rows); the band's input rows [h_lo, h_hi) are staged in shared memory
+// KT / ST: compile-time kernel size and stride (0 = run-time values): with run-time loop bounds the pooling loops
+// compiled to ~50 instructions per output and the kernel was issue-bound (ncu: issue slots 89 % busy at 2.4 TB/s).
+template <int KT, int ST>
+__global__ void __launch_bounds__(kPoolThreads)
+maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int P, int Q, int k_rt, int stride_rt, int pad,
+                 int band_rows, int bands, int in_rows_alloc) {
+    const int k = KT ? KT : k_rt, stride = ST ? ST : stride_rt;
+    extern __shared__ float tile[];
+    const int plane = blockIdx.x / bands, band = blockIdx.x - plane * bands;
+    const int p0 = band * band_rows, p1 = min(P, p0 + band_rows);
+    const int h_lo = max(0, p0 * stride - pad), h_hi = min(H, (p1 - 1) * stride - pad + k);
+    const float* xp = x + (int64_t)plane * H * W + (int64_t)h_lo * W;
+    const int n_in = (h_hi - h_lo) * W;
+    if ((reinterpret_cast<uintptr_t>(xp) & 15) == 0 && (n_in & 3) == 0) {
+        const float4* x4 = reinterpret_cast<const float4*>(xp);
+        float4* t4 = reinterpret_cast<float4*>(tile);
+        const int n4 = n_in >> 2;
+        // eight independent 16-byte loads per thread in flight before the first shared-memory store: a loop of
+        // load -> store pairs serialises one DRAM round trip per iteration and the block spends its life waiting
+        for (int base = 0; base < n4; base += 8 * kPoolThreads) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * kPoolThreads + threadIdx.x;
+                if (i < n4)
+                    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                        : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(x4 + i));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * kPoolThreads + threadIdx.x;
+                if (i < n4) t4[i] = v[u];
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_in; i += kPoolThreads) tile[i] = __ldg(xp + i);
+    }
+    __syncthreads();
+    // separable: each warp takes output rows p0 + warp, p0 + warp + 8, ...; it first reduces the k input rows of an
+    // output row column-wise (consecutive lanes = consecutive columns: conflict-free) into its own row of vbuf, then
+    // reduces k neighbours of that row per output column.  Only the warp itself reads its vbuf row -> __syncwarp.
+    float* vbuf = tile + (size_t)in_rows_alloc * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* op = out + (int64_t)plane * P * Q;
+    for (int p = p0 + warp; p < p1; p += kPoolThreads / 32) {
+        const int h0 = p * stride - pad;
+        const int r_lo = max(0, -h0), r_hi = min(k, H - h0);
+        float* vrow = vbuf + (size_t)(p - p0) * W;
+        const float* trow = tile + (h0 - h_lo) * W;   // row r of the window = trow + r * W (only rows r_lo..r_hi-1 are staged)
+        for (int w = lane; w < W; w += 32) {
+            float m = -INFINITY;
+            if (KT) {
+#pragma unroll
+                for (int r = 0; r < (KT ? KT : 1); ++r)
+                    if (r >= r_lo && r < r_hi) m = max_nan(m, trow[r * W + w]);
+            } else {
+                for (int r = r_lo; r < r_hi; ++r) m = max_nan(m, trow[r * W + w]);
+            }
+            vrow[w] = m;
+        }
+        __syncwarp();
+        for (int q = lane; q < Q; q += 32) {
+            const int w0 = q * stride - pad;
+            float m = -INFINITY;
+            if (KT) {
+#pragma unroll
+                for (int s2 = 0; s2 < (KT ? KT : 1); ++s2)
+                    if (w0 + s2 >= 0 && w0 + s2 < W) m = max_nan(m, vrow[w0 + s2]);
+            } else {
+                for (int s2 = max(0, -w0); s2 < min(k, W - w0); ++s2) m = max_nan(m, vrow[w0 + s2]);
+            }
+            op[(int64_t)p * Q + q] = m;
+        }
+    }
+}
+
+}  // namespace
+}  // namespace qb200
+
+extern "C" int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, int32_t W, int32_t kernel, int32_t stride,
+                                   int32_t pad, float* out, void* stream) {
+    using namespace qb200;
+    QB_REQUIRE(x && out, QB200_EINVAL, "maxpool2d: null pointer");
+    QB_REQUIRE(kernel >= 1 && stride >= 1 && pad >= 0 && 2 * pad <= kernel && H >= 1 && W >= 1, QB200_EINVAL,
+               "maxpool2d: bad geometry");
+    const int P = (H + 2 * pad - kernel) / stride + 1, Q = (W + 2 * pad - kernel) / stride + 1;
+    QB_REQUIRE(P >= 1 && Q >= 1, QB200_EINVAL, "maxpool2d: empty output");
+    if (planes == 0) return 0;
+    // as many output rows per block as keep the staged input rows within 32 KB (+ the column-reduced rows: ~5 blocks per SM)
+    const int max_in_rows = std::max(kernel, (32 * 1024) / (W * 4));
+    QB_REQUIRE((size_t)kernel * W * 4 <= 200 * 1024, QB200_EUNSUPPORTED, "maxpool2d: rows wider than shared memory allows");
+    int band_rows = std::max(1, (max_in_rows - kernel) / stride + 1);
+    band_rows = std::min(band_rows, P);
+    int bands = (P + band_rows - 1) / band_rows;
+    band_rows = (P + bands - 1) / bands;  // balance the bands
+    bands = (P + band_rows - 1) / band_rows;
+    const int in_rows = std::min(H, (band_rows - 1) * stride + kernel);
+    const size_t smem = ((size_t)in_rows + band_rows) * W * 4;  // staged input rows + one column-reduced row per output row
+    QB_REQUIRE(planes * bands < (1ll << 31), QB200_EINVAL, "maxpool2d: too many blocks");
+    auto launch = [&](auto kern) -> int {
+        QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<(unsigned)(planes * bands), kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+            x, out, H, W, P, Q, kernel, stride, pad, band_rows, bands, in_rows);
+        return 0;
+    };
+    if (kernel == 3 && stride == 2) { if (int rc = launch(maxpool2d_kernel<3, 2>)) return rc; }
+    else if (kernel == 2 && stride == 2) { if (int rc = launch(maxpool2d_kernel<2, 2>)) return rc; }
+    else if (kernel == 3 && stride == 1) { if (int rc = launch(maxpool2d_kernel<3, 1>)) return rc; }
+    else { if (int rc = launch(maxpool2d_kernel<0, 0>)) return rc; }
+    QB_LAUNCH_CHECK();
+    return 0;
+}

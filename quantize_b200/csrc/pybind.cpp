@@ -335,9 +335,183 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
     qb200_conv_tail tail;
     tail.residual = residual.has_value() ? residual.value().data_ptr<float>() : nullptr;
     tail.relu = fuse_relu ? 1 : 0;
+    tail.next_shape = nullptr;
+    tail.next_quant = nullptr;
+    tail.next_workspace = nullptr;
     check_rc(qb200_quantconv2d_fused_ex(&s, input.data_ptr<float>(), pw->buffer.data_ptr(), weight_scale.data_ptr<float>(),
                                         (int32_t)n_ws, bias_p, &aq, &tail, ws.data_ptr(), out.data_ptr(), QB200_OUT_F32, st),
              "quantconv2d_float_input");
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// quantconv2d_chain (engine extension, SURVEY §8(f) next-1: int8 activations between layers)
+//
+// Runs consecutive fused convs  x -> L0 -> [relu] -> L1 -> [relu] -> ... -> L(n-1) -> (+ residual) -> [relu]  where each
+// intermediate result is handed to the next layer already quantized with that layer's activation quantizer (written
+// by the producer's epilogue into the consumer's workspace) instead of as an fp32 tensor.  The result is bit-identical
+// to calling quantconv2d_float_input layer by layer: the same fp32 value goes through the same quantizer arithmetic.
+// Each element of `layers` is a tuple
+//   (weight, weight_des, weight_scale, weight_zero, bias|None, stride, padding,
+//    input_scale, input_zero, input_qmin, input_qmax, relu_after)
+// Pairs the engine cannot chain (qb200_conv_handoff_supported) fall back to an fp32 intermediate.
+// emit_next = such a tuple for the layer that will consume this chain's RESULT: the last epilogue then writes the fp32
+// result (the residual path needs it) and the consumer's quantized workspace; the call returns (out, workspace|None)
+// and a later chain starting with that layer takes the workspace as input_handoff (its `input` is then only used for
+// the shape).
+// ------------------------------------------------------------------------------------------------
+struct ChainLayer {
+    at::Tensor weight, des, scale, zero;
+    c10::optional<at::Tensor> bias;
+    qb200_conv_shape s;
+    int32_t P, Q;
+    qb200_act_quant aq;
+    PreparedWeights* pw;
+    bool relu;
+};
+
+py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, const c10::optional<at::Tensor>& residual,
+                             const c10::optional<at::Tensor>& input_handoff, const py::object& emit_next) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
+    const size_t n = layers.size();  // layers of the chain proper; an optional extra entry describes emit_next's consumer
+    TORCH_CHECK(n >= 1, "quantconv2d_chain: no layers");
+    const bool emit = !emit_next.is_none();
+    c10::cuda::CUDAGuard guard(input.device());
+    std::lock_guard<std::mutex> lock(g_mu);
+    void* st = cur_stream();
+    std::vector<at::Tensor> keep;
+    std::vector<ChainLayer> L(n + (emit ? 1 : 0));
+    int32_t N = (int32_t)input.size(0), C = (int32_t)input.size(1), H = (int32_t)input.size(2), W = (int32_t)input.size(3);
+    for (size_t i = 0; i < L.size(); ++i) {
+        const py::tuple t = (i < n ? py::object(layers[i]) : emit_next).cast<py::tuple>();
+        TORCH_CHECK(t.size() == 12, "quantconv2d_chain: each layer is a 12-tuple");
+        ChainLayer& l = L[i];
+        l.weight = t[0].cast<at::Tensor>();
+        l.des = t[1].cast<at::Tensor>();
+        l.scale = t[2].cast<at::Tensor>();
+        l.zero = t[3].cast<at::Tensor>();
+        if (!t[4].is_none()) l.bias = t[4].cast<at::Tensor>();
+        CHECK_INPUT(l.weight);
+        CHECK_INPUT(l.des);
+        CHECK_INPUT(l.scale);
+        CHECK_INPUT(l.zero);
+        TORCH_CHECK(l.weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
+        CHECK_FLOAT(l.scale);
+        CHECK_FLOAT(l.zero);
+        if (l.bias.has_value()) {
+            CHECK_INPUT(l.bias.value());
+            TORCH_CHECK(l.bias.value().dtype() == torch::kFloat32, "bias must be a float tensor");
+        }
+        const std::vector<int64_t>& d = host_des(l.des);
+        TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+        qb200_conv_shape& s = l.s;
+        s.N = N; s.C = C; s.H = H; s.W = W;
+        s.w_bits = (int32_t)d[0];
+        s.w_sign = d[1] != 0;
+        s.K = (int32_t)d[2]; s.Cg = (int32_t)d[3]; s.R = (int32_t)d[4]; s.S = (int32_t)d[5];
+        s.stride = t[5].cast<int>();
+        s.pad = t[6].cast<int>();
+        check_rc(qb200_conv_out_hw(&s, &l.P, &l.Q), "quantconv2d_chain");
+        TORCH_CHECK(l.weight.numel() >= qb200_packed_bytes((int64_t)s.K * s.Cg * s.R * s.S, s.w_bits),
+                    "weight is shorter than weight_des describes");
+        const int64_t n_ws = l.scale.numel();
+        TORCH_CHECK(n_ws == 1 || n_ws == s.K, "weight_scale must have 1 or ", s.K, " elements");
+        TORCH_CHECK(l.zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
+        if (l.bias.has_value()) TORCH_CHECK(l.bias.value().numel() == s.K, "bias must have ", s.K, " elements");
+        const Key wk = key_of(l.weight, l.des.data_ptr());
+        l.pw = g_prep_cache.find(wk, l.weight);
+        if (!l.pw) {
+            PreparedWeights fresh;
+            fresh.buffer = at::empty({(int64_t)qb200_conv_prepared_bytes(&s)}, l.weight.options());
+            check_rc(qb200_conv_prepare_weights(&s, l.weight.data_ptr<uint8_t>(), fresh.buffer.data_ptr(), st), "prepare_weights");
+            fresh.zero_is_zero = l.zero.abs().max().item<float>() == 0.f;
+            l.pw = g_prep_cache.insert(wk, l.weight, std::move(fresh));
+        }
+        TORCH_CHECK(l.pw->zero_is_zero, "quantconv2d_chain needs symmetric weights (weight_zero == 0)");
+        l.aq.scale = device_float(t[7], input.device(), keep, "input_scale");
+        l.aq.zero = device_float(t[8], input.device(), keep, "input_zero");
+        l.aq.qmin = device_float(t[9], input.device(), keep, "input_qmin");
+        l.aq.qmax = device_float(t[10], input.device(), keep, "input_qmax");
+        l.relu = t[11].cast<bool>();
+        C = s.K; H = l.P; W = l.Q;
+    }
+    if (residual.has_value()) {
+        const at::Tensor& r = residual.value();
+        CHECK_INPUT(r);
+        const ChainLayer& e = L[n - 1];
+        TORCH_CHECK(r.dtype() == torch::kFloat32 && r.dim() == 4 && r.size(0) == N && r.size(1) == e.s.K && r.size(2) == e.P &&
+                        r.size(3) == e.Q, "residual must be a float tensor shaped like the output");
+    }
+    at::Tensor x = input;          // fp32 input of the current layer (when not handed off)
+    at::Tensor ws_in;              // quantized workspace of the current layer (when handed off)
+    bool handed = false;
+    if (input_handoff.has_value()) {
+        // the first layer's input arrives already quantized (written by an earlier chain's emit_next for this very layer)
+        const at::Tensor& h = input_handoff.value();
+        CHECK_INPUT(h);
+        TORCH_CHECK(h.dtype() == torch::kByte && (size_t)h.numel() >= qb200_conv_workspace_bytes(&L[0].s),
+                    "input_handoff is not a workspace of the first layer");
+        ws_in = h;
+        handed = true;
+    }
+    at::Tensor out, ws_emit;
+    for (size_t i = 0; i < n; ++i) {
+        ChainLayer& l = L[i];
+        const bool last = i + 1 == n;
+        const float* bias_p = l.bias.has_value() ? l.bias.value().data_ptr<float>() : nullptr;
+        qb200_conv_tail tail;
+        tail.residual = (last && residual.has_value()) ? residual.value().data_ptr<float>() : nullptr;
+        tail.relu = l.relu ? 1 : 0;
+        tail.next_shape = nullptr;
+        tail.next_quant = nullptr;
+        tail.next_workspace = nullptr;
+        at::Tensor ws_next;
+        // the last layer hands over only on request (emit_next) and then writes BOTH the fp32 result and the bytes
+        const bool hand = (!last || emit) && qb200_conv_handoff_supported(&l.s, &L[i + 1].s) != 0;
+        if (hand) {
+            ws_next = at::empty({(int64_t)qb200_conv_workspace_bytes(&L[i + 1].s)}, l.weight.options());
+            tail.next_shape = &L[i + 1].s;
+            tail.next_quant = &L[i + 1].aq;
+            tail.next_workspace = ws_next.data_ptr();
+        }
+        if (!hand || last) out = at::empty({l.s.N, l.s.K, l.P, l.Q}, input.options());
+        void* out_p = (hand && !last) ? nullptr : out.data_ptr();
+        if (last && hand) ws_emit = ws_next;
+        if (handed) {
+            check_rc(qb200_conv_from_workspace_ex(&l.s, ws_in.data_ptr(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
+                                                  (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, out_p, QB200_OUT_F32, st),
+                     "quantconv2d_chain");
+        } else {
+            auto ws = at::empty({(int64_t)qb200_conv_workspace_bytes(&l.s)}, l.weight.options());
+            check_rc(qb200_quantconv2d_fused_ex(&l.s, x.data_ptr<float>(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
+                                                (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, ws.data_ptr(), out_p,
+                                                QB200_OUT_F32, st),
+                     "quantconv2d_chain");
+        }
+        handed = hand;
+        if (hand) ws_in = ws_next;
+        else x = out;
+    }
+    if (!emit) return py::cast(out);
+    return py::make_tuple(out, ws_emit.defined() ? py::cast(ws_emit) : py::none());
+}
+
+// max_pool2d (engine helper for the packed ResNet forward; same result as torch.nn.functional.max_pool2d)
+at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int padding) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
+    c10::cuda::CUDAGuard guard(input.device());
+    const int H = (int)input.size(2), W = (int)input.size(3);
+    TORCH_CHECK(kernel >= 1 && stride >= 1 && padding >= 0 && 2 * padding <= kernel, "max_pool2d: bad geometry");
+    const int P = (H + 2 * padding - kernel) / stride + 1, Q = (W + 2 * padding - kernel) / stride + 1;
+    TORCH_CHECK(P >= 1 && Q >= 1, "max_pool2d: empty output");
+    auto out = at::empty({input.size(0), input.size(1), P, Q}, input.options());
+    check_rc(qb200_maxpool2d_f32(input.data_ptr<float>(), input.size(0) * input.size(1), H, W, kernel, stride, padding,
+                                 out.data_ptr<float>(), cur_stream()),
+             "max_pool2d");
     return out;
 }
 
@@ -383,6 +557,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("bias"), py::arg("stride"), py::arg("padding"), py::arg("input_scale") = py::none(),
           py::arg("input_zero") = py::none(), py::arg("input_qmin") = py::none(), py::arg("input_qmax") = py::none(),
           py::arg("residual") = py::none(), py::arg("fuse_relu") = false);
+    m.def("quantconv2d_chain", &quantconv2d_chain,
+          "Consecutive fused quantized convs with int8 activations handed from one layer's epilogue to the next.",
+          py::arg("input"), py::arg("layers"), py::arg("residual") = py::none(), py::arg("input_handoff") = py::none(),
+          py::arg("emit_next") = py::none());
+    m.def("max_pool2d", &max_pool2d, "fp32 NCHW max pooling (square kernel / stride, -inf padding, floor mode).",
+          py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0);
     // engine-level helpers (not part of the reference surface)
     m.def("_launch_count", []() { return (uint64_t)qb200_launch_count(); });
     m.def("_launch_count_reset", []() { qb200_launch_count_reset(); });

@@ -206,6 +206,17 @@ class QuantConv2d(nn.Conv2d):
         self.w_quantizer = None
         self.packed = True
 
+    def symmetric_weights(self) -> bool:
+        if not hasattr(self, "_w_sym"):
+            self._w_sym = bool((self.w_zero == 0).all().item())
+        return self._w_sym
+
+    def chain_args(self):
+        """this layer as an element of engine.quantconv2d_chain's `layers` (the op's arguments + relu-after flag)."""
+        a = self.a_quantizer
+        return (self.weight, self.w_des, self.w_scale, self.w_zero, self.bias, self.stride[0], self.padding[0],
+                a.scale, a.zero, a.qmin, a.qmax, bool(self.fuse_relu))
+
     def forward(self, x: Tensor, residual: Tensor = None) -> Tensor:    # quantconv2d.py:198-210
         """`residual` / `self.fuse_relu` are this mirror's extension: out = relu(out + residual) in the conv's epilogue
         (bit-identical to the separate torch ops, which is what every non-engine branch below executes)."""
@@ -227,37 +238,96 @@ class QuantConv2d(nn.Conv2d):
         return torch.relu(out) if self.fuse_relu else out
 
 
-def _bottleneck_forward(self, x):
-    """torchvision.models.resnet.Bottleneck.forward with the ReLUs and the residual add folded into the convs."""
-    out = self.conv2(self.conv1(x))
+class EngineMaxPool2d(nn.Module):
+    """nn.MaxPool2d (square kernel / stride, no dilation, floor mode) on the engine's kernel; same values as torch."""
+
+    def __init__(self, pool: nn.MaxPool2d):
+        super().__init__()
+        one = lambda v: v if isinstance(v, int) else v[0]
+        assert not pool.ceil_mode and one(pool.dilation) == 1 and not pool.return_indices
+        self.kernel_size, self.stride, self.padding = one(pool.kernel_size), one(pool.stride or pool.kernel_size), one(pool.padding)
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32:
+            return _engine.load().max_pool2d(x.contiguous(), self.kernel_size, self.stride, self.padding)
+        return torch.nn.functional.max_pool2d(x, self.kernel_size, self.stride, self.padding)
+
+
+def _chainable(convs):
+    """int8 hand-off between consecutive convs needs the engine path and symmetric weights (w_zero == 0)."""
+    return all(c.packed and c.use_engine and c.symmetric_weights() for c in convs)
+
+
+def _block_convs(block):
+    return (block.conv1, block.conv2, block.conv3) if hasattr(block, "conv3") else (block.conv1, block.conv2)
+
+
+def _block_forward(self, x, handoff=None, next_conv=None):
+    """torchvision Bottleneck / BasicBlock forward with the ReLUs and the residual add folded into the convs.
+    With `self.chain` the convs run as ONE engine chain: each conv hands its (ReLU'd) result to the next one already
+    quantized, so the intermediates never exist as fp32 tensors (same bits as the unchained path).
+    handoff / next_conv (used by _stage_forward): the block's input as the int8 workspace the previous block wrote for
+    conv1, and the conv that will consume this block's output — the last epilogue then writes fp32 + int8."""
     identity = x if self.downsample is None else self.downsample(x)
-    return self.conv3(out, residual=identity)
+    convs = _block_convs(self)
+    if getattr(self, "chain", False) and _chainable(convs):
+        qe = _engine.load()
+        layers = [c.chain_args() for c in convs]
+        if next_conv is not None and _chainable((next_conv,)):
+            return qe.quantconv2d_chain(x.contiguous(), layers, residual=identity.contiguous(), input_handoff=handoff,
+                                        emit_next=next_conv.chain_args())
+        out = qe.quantconv2d_chain(x.contiguous(), layers, residual=identity.contiguous(), input_handoff=handoff)
+        return out if next_conv is None else (out, None)
+    out = x
+    for c in convs[:-1]:
+        out = c(out)
+    out = convs[-1](out, residual=identity)
+    return out if next_conv is None else (out, None)
 
 
-def _basicblock_forward(self, x):
-    """torchvision.models.resnet.BasicBlock.forward, same folding."""
-    out = self.conv1(x)
-    identity = x if self.downsample is None else self.downsample(x)
-    return self.conv2(out, residual=identity)
+def _stage_forward(self, x):
+    """nn.Sequential of residual blocks: block i's last conv also writes the int8 input of block i+1's conv1 (when that
+    block has an identity shortcut, i.e. conv1 is the only quantizing consumer besides the fp32 residual path)."""
+    blocks = list(self)
+    handoff = None
+    for i, blk in enumerate(blocks):
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        if nxt is not None and getattr(blk, "chain", False) and getattr(nxt, "chain", False):
+            x, handoff = blk(x, handoff, nxt.conv1)
+        else:
+            x = blk(x, handoff)
+            handoff = None
+    return x
 
 
-def fuse_resnet_blocks(model):
+def fuse_resnet_blocks(model, chain=False, cross_block=False):
     """For torchvision ResNets rebuilt with QuantConv2d: run `relu` and `+ identity` in the conv epilogues.
     Every fused conv applies relu(out [+ residual]) exactly where the original block does, so the network function is
-    unchanged (tests/test_models_gpu.py asserts bit-identical logits)."""
+    unchanged (tests/test_models_gpu.py asserts bit-identical logits).  chain=True additionally keeps the activations
+    between the convs of a block quantized (engine.quantconv2d_chain); cross_block=True also lets a block's last conv
+    write the int8 input of the next block's conv1 next to its fp32 result (measured slower on ResNet-50 at batch 256:
+    the dual-output epilogue costs more than the quantizer launch it replaces — kept for tests and smaller batches)."""
     import types
     import torchvision.models.resnet as R
     for m in model.modules():
         if isinstance(m, R.Bottleneck) and all(isinstance(c, QuantConv2d) for c in (m.conv1, m.conv2, m.conv3)):
             for c in (m.conv1, m.conv2, m.conv3):
                 c.fuse_relu = True
-            m.forward = types.MethodType(_bottleneck_forward, m)
+            m.chain = chain
+            m.forward = types.MethodType(_block_forward, m)
         elif isinstance(m, R.BasicBlock) and all(isinstance(c, QuantConv2d) for c in (m.conv1, m.conv2)):
             m.conv1.fuse_relu = m.conv2.fuse_relu = True
-            m.forward = types.MethodType(_basicblock_forward, m)
+            m.chain = chain
+            m.forward = types.MethodType(_block_forward, m)
+    if chain and cross_block and isinstance(model, R.ResNet):
+        for stage in (model.layer1, model.layer2, model.layer3, model.layer4):
+            if all(hasattr(b, "chain") for b in stage):
+                stage.forward = types.MethodType(_stage_forward, stage)
     if isinstance(model, R.ResNet) and isinstance(model.conv1, QuantConv2d):
         model.conv1.fuse_relu = True        # stem: conv1 -> (folded bn) -> relu -> maxpool
         model.relu = nn.Identity()
+        if isinstance(model.maxpool, nn.MaxPool2d) and not model.maxpool.ceil_mode:
+            model.maxpool = EngineMaxPool2d(model.maxpool)
     return model
 
 

@@ -92,14 +92,15 @@ def synthetic_batch(name, batch, seed=1, device="cpu"):
     return torch.randn(batch, 3, hw, hw, generator=g).to(device)
 
 
-def build_packed(name, w_bits=8, a_bits=8, calib_batch=8, device="cuda", seed=0, fuse_blocks=False):
+def build_packed(name, w_bits=8, a_bits=8, calib_batch=8, device="cuda", seed=0, fuse_blocks=False, chain_blocks=False, cross_block=False):
     """calibrate on a synthetic batch (one PTQ pass), pack every conv with the engine's tpack; ready for inference.
-    fuse_blocks: fold ReLU / residual add of torchvision ResNet blocks into the conv epilogues (same function)."""
+    fuse_blocks: fold ReLU / residual add of torchvision ResNet blocks into the conv epilogues (same function);
+    chain_blocks: also hand the activations between the convs of a block over as int8 (engine.quantconv2d_chain)."""
     model = build_quantized(name, w_bits, a_bits, seed).to(device)
     host.calibrate(model, synthetic_batch(name, calib_batch, seed + 1, device))
     host.pack(model)
-    if fuse_blocks:
-        host.fuse_resnet_blocks(model)
+    if fuse_blocks or chain_blocks:
+        host.fuse_resnet_blocks(model, chain=chain_blocks, cross_block=cross_block)
     return model
 
 

@@ -101,6 +101,89 @@ def test_fused_blocks_are_bit_identical(name, batch):
     assert torch.equal(ref_path.argmax(1), want.argmax(1))
 
 
+@pytest.mark.parametrize("cross", [False, True], ids=["in-block", "cross-block"])
+@pytest.mark.parametrize("name,batch,wb,ab", [("resnet18", 4, 8, 8), ("resnet50", 3, 8, 8), ("resnet50", 2, 4, 4),
+                                              ("resnet20", 5, 8, 8)])
+def test_chained_blocks_are_bit_identical(name, batch, wb, ab, cross):
+    """int8 activations handed from one conv's epilogue to the next conv (quantconv2d_chain)
+    give the same logits, bit for bit, as the layer-by-layer fp32 hand-over."""
+    import quantize_b200.engine as E
+    model = models.build_packed(name, wb, ab, calib_batch=4, fuse_blocks=True)
+    x = models.synthetic_batch(name, batch, device="cuda")
+    with torch.no_grad():
+        want = model(x)
+        chained = host.fuse_resnet_blocks(copy.deepcopy(model), chain=True, cross_block=cross)
+        qe = E.load()
+        chained(x)                    # (the first call prepares the copied weights)
+        qe._launch_count_reset()
+        got = chained(x)
+        n_chain = qe._launch_count()
+        qe._launch_count_reset()
+        model(x)
+        n_plain = qe._launch_count()
+    assert torch.equal(got, want)
+    if name != "resnet20":      # (its blocks are not torchvision's: nothing to chain, still must run)
+        assert n_chain < n_plain      # the intermediate quantizer launches are gone
+
+
+def test_chain_op_level_all_layouts(engine):
+    """quantconv2d_chain == quantconv2d_float_input applied layer by layer, for every consumer workspace layout:
+    NHWC (1x1 and strided 3x3 consumers), zero-padded NHWC (halo variant), ragged channel counts, zero points != 0,
+    and a pair the engine cannot chain (depthwise consumer -> fp32 fallback inside the chain)."""
+    from gpu_util import random_conv_case
+    import numpy as np
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    # (C0, H, [ (K, R, stride, pad, groups), ... ])
+    nets = [
+        (64, 28, [(64, 1, 1, 0, 1), (64, 3, 1, 1, 1), (256, 1, 1, 0, 1)]),      # bottleneck, halo consumer (C=64, 28x28)
+        (128, 14, [(128, 3, 2, 1, 1), (128, 3, 1, 1, 1)]),                       # strided producer, plain consumers
+        (24, 9, [(40, 3, 1, 1, 1), (72, 1, 1, 0, 1), (24, 3, 1, 1, 1)]),         # ragged channels (Cp > C)
+        (3, 33, [(64, 7, 2, 3, 1), (32, 3, 1, 1, 1)]),                           # im2col-rows producer (stem)
+        (32, 10, [(32, 1, 1, 0, 1), (32, 3, 1, 1, 32), (16, 1, 1, 0, 1)]),       # depthwise in the middle: fp32 fallback
+        (256, 7, [(64, 1, 2, 0, 1), (64, 1, 1, 0, 1)]),                          # strided 1x1 producer
+    ]
+    for algo in (0, 4):
+        engine._set_conv_algo(algo)
+        try:
+            for seed, (C0, H, layers) in enumerate(nets):
+                if algo == 4 and any(l[4] > 1 for l in layers):
+                    continue              # (forcing the tensor-core variants excludes grouped convs)
+                N = 3
+                g = torch.Generator().manual_seed(seed)
+                x = torch.randn(N, C0, H, H, generator=g).cuda()
+                C, Hc = C0, H
+                tuples, cur = [], x
+                want = x
+                for li, (K, R, stride, pad, groups) in enumerate(layers):
+                    c = random_conv_case(100 * seed + li, N, C, Hc, Hc, K, R, stride, pad, groups)
+                    relu = li % 2 == 0
+                    # asymmetric per-tensor quantizer fitted to this layer's input (range/minmax.py:136-143)
+                    lo_, hi_ = float(want.min()), float(want.max())
+                    a_scale = torch.tensor([(hi_ - lo_) / 255.0], dtype=torch.float32).cuda()
+                    a_zero = (torch.tensor([lo_], dtype=torch.float32).cuda() / a_scale) if li != 1 else torch.zeros(1).cuda()
+                    tup = (t(c["packed"]), t(c["des"]), t(c["w_scale"]), torch.zeros(K).cuda(), t(c["bias"]), stride, pad,
+                           a_scale, a_zero, 0, 255, relu)
+                    tuples.append(tup)
+                    want = engine.quantconv2d_float_input(want, *tup[:7], input_scale=a_scale, input_zero=a_zero,
+                                                          input_qmin=0, input_qmax=255, fuse_relu=relu)
+                    C, Hc = K, want.shape[2]
+                got = engine.quantconv2d_chain(x, tuples)
+                assert torch.equal(got, want), (algo, seed)
+                res = torch.randn_like(want)
+                last = tuples[-1]
+                want_r = None
+                # residual on the last layer
+                prev = x
+                for tup in tuples[:-1]:
+                    prev = engine.quantconv2d_float_input(prev, *tup[:7], input_scale=tup[7], input_zero=tup[8], input_qmin=0,
+                                                          input_qmax=255, fuse_relu=tup[11])
+                want_r = engine.quantconv2d_float_input(prev, *last[:7], input_scale=last[7], input_zero=last[8], input_qmin=0,
+                                                        input_qmax=255, residual=res, fuse_relu=last[11])
+                assert torch.equal(engine.quantconv2d_chain(x, tuples, residual=res), want_r), (algo, seed, "residual")
+        finally:
+            engine._set_conv_algo(0)
+
+
 def test_fused_tail_op_level(engine):
     """quantconv2d_float_input(..., residual=, fuse_relu=) == relu(op(...) + residual), both conv kernels."""
     from gpu_util import random_conv_case
