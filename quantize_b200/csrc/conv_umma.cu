@@ -41,7 +41,7 @@ constexpr int kTailBytes = kBarBytes + 2 * kConstFloats * 4;  // barriers + two 
 constexpr int kMaxWclsBytes = 16 * 1024;                 // one buffer of per-window-class channel sums (layers with R*S > 1)
 constexpr int kMaxCls = 16;                              // distinct row (and column) windows supported by the class table
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;     // TMEM columns between the two accumulator buffers
+constexpr int kMaxAcc = 4;          // accumulator buffers in TMEM: 2 x 256 columns, or 4 x 128 when the tile has <= 128 channels
 constexpr int kMaxStages = 24;      // small stages (weight-only tiles of the halo variant) need depth to cover TMA latency
 constexpr size_t kSmemBudget = 200 * 1024;
 constexpr size_t kSmemBudgetFq = 224 * 1024;  // the fused-quantize variant wants every byte for fp32 tiles in flight
@@ -95,6 +95,7 @@ struct UmmaParams {
     int halo;          // 0/1
     int Hp, Wp, halo_rows, halo_bytes, h_stages;
     int x_stages;  // fused-quantize variant: slots of the fp32 ring
+    int n_acc, acc_stride;  // TMEM accumulator buffers and the columns between them
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
     int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
     const float* x;
@@ -310,9 +311,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)x_slots * x_bytes);
     uint64_t* full = bars;                     // [stages]
     uint64_t* empty = bars + kMaxStages;       // [stages]
-    uint64_t* acc_full = bars + 2 * kMaxStages;      // [2]
-    uint64_t* acc_empty = bars + 2 * kMaxStages + 2; // [2]
-    uint64_t* xfull = bars + 2 * kMaxStages + 4;     // [kMaxXStages]
+    uint64_t* acc_full = bars + 2 * kMaxStages;               // [kMaxAcc]
+    uint64_t* acc_empty = bars + 2 * kMaxStages + kMaxAcc;    // [kMaxAcc]
+    uint64_t* xfull = bars + 2 * kMaxStages + 2 * kMaxAcc;  // [kMaxXStages]
     uint64_t* xempty = xfull + kMaxXStages;          // [kMaxXStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kMaxXStages);
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][3][256]
@@ -330,7 +331,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             mbar_init(&full[i], kFQ ? 1 + kFqWarps : 1);  // TMA expect_tx arrival (+ one arrival per quantizer warp)
             mbar_init(&empty[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kMaxAcc; ++i) {
             mbar_init(&acc_full[i], 1);
             mbar_init(&acc_empty[i], kEpiWarps);
         }
@@ -431,7 +432,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait<kFQ ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * kAccStride);
+            const uint32_t tmem_d = tmem_base + (uint32_t)(buf * prm.acc_stride);
             uint32_t accumulate = 0;
             if (halo) {
                 for (int cb = 0; cb < cblocks; ++cb) {
@@ -478,7 +479,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             if (lane == 0) umma_commit(&acc_full[buf]);  // accumulator complete
             __syncwarp();
-            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            if (++buf == prm.n_acc) { buf = 0; acc_phase ^= 1; }
         }
     } else if (kFQ && warp == 2 + kEpiWarps) {
         // ===================== TMA producer of the fp32 input tiles (fused-quantize variant) =====================
@@ -593,13 +594,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int n_tile = tile - m_tile * prm.n_tiles;
             const int k_base = n_tile * BN;
             // ---- per-tile channel constants (once per CTA when there is a single channel tile) ----
-            float* sc = consts + (prm.n_tiles > 1 ? buf : 0) * kConstFloats;
+            float* sc = consts + (prm.n_tiles > 1 ? (iter & 1) : 0) * kConstFloats;   // two constant buffers, by tile parity
             float* be = sc + 256;
             float* br = sc + 512;
             const int tbl = (g.R + 1) * (g.S + 1);
             const int32_t* wtab = ep.wpre + (int64_t)k_base * tbl;  // prefix tables of this tile's channels
             const bool use_cls = prm.wcls_smem > 0 && es.z_a != 0.f;
-            float* wcls = wcls_s + (prm.n_tiles > 1 ? buf : 0) * (prm.wcls_smem / 4);
+            float* wcls = wcls_s + (prm.n_tiles > 1 ? (iter & 1) : 0) * (prm.wcls_smem / 4);
             if (iter == 0 || prm.n_tiles > 1) {
                 if (use_cls) {
                     const int s1c = g.S + 1;
@@ -673,7 +674,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (kFQ) mbar_wait_sleepy<500>(&acc_full[buf], acc_phase, prm.err_flag, 4);
             else mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccStride + half * cols);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * prm.acc_stride + half * cols);
             for (int c0 = 0; c0 < cols; c0 += 32) {
                 const int cc = half * cols + c0;  // first column of this chunk inside the tile
                 // optional fused tail (beyond the reference op): out = relu(out + residual), rounded like the separate
@@ -835,7 +836,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+            if (++buf == prm.n_acc) { buf = 0; acc_phase ^= 1; }
         }
     }
 
@@ -1000,6 +1001,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
     while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
     prm.BN = BN;
+    // more tiles in flight where they are small: the MMA of tile i+3 need not wait for the epilogue of tile i+1
+    prm.n_acc = BN <= 128 ? 4 : 2;
+    prm.acc_stride = kTmemCols / prm.n_acc;
     prm.n_tiles = (g.K + BN - 1) / BN;
     prm.fd_ntiles = make_fastdiv(prm.n_tiles);
     // halo variant: a weight stage holds the tiles of tap_group taps (all taps, one filter row, or one tap — the largest
