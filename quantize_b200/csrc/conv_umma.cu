@@ -44,6 +44,9 @@ constexpr int kTmemCols = 512;
 constexpr int kMaxAcc = 4;          // accumulator buffers in TMEM: 2 x 256 columns, or 4 x 128 when the tile has <= 128 channels
 constexpr int kMaxStages = 24;      // small stages (weight-only tiles of the halo variant) need depth to cover TMA latency
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr int kResDepth = 3;                            // residual chunks in flight per epilogue warp (cp.async ring)
+constexpr int kResChunkFloats = 32 * 32;                // one chunk: 32 channels x 32 pixels
+constexpr size_t kResBytes = (size_t)kEpiWarps * kResDepth * kResChunkFloats * 4;  // 96 KB
 constexpr size_t kSmemBudgetFq = 224 * 1024;  // the fused-quantize variant wants every byte for fp32 tiles in flight
 
 // Division of a non-negative 32-bit value by a launch-time constant as one multiply-high + shift: the per-tile index
@@ -96,6 +99,7 @@ struct UmmaParams {
     int Hp, Wp, halo_rows, halo_bytes, h_stages;
     int x_stages;  // fused-quantize variant: slots of the fp32 ring
     int n_acc, acc_stride;  // TMEM accumulator buffers and the columns between them
+    int res_async;          // residual tail: stream the identity tensor through a per-warp cp.async ring
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
     int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
     const float* x;
@@ -117,6 +121,12 @@ __device__ __forceinline__ float4 lds4(const float* p) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
     return v;
 }
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -587,6 +597,48 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         QuantParams q8p = {};
         if (!kFQ && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
         const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
+        // ---- residual stream (fused tail) ----
+        // The identity tensor is the largest read of a residual layer and a warp that loads one 32-channel chunk at a
+        // time keeps too few bytes in flight for HBM latency (ncu: 40 % of the epilogue's samples waited on those
+        // loads).  Each warp therefore streams ITS chunks — in the order it will consume them, across tiles — through a
+        // private cp.async ring, kResDepth - 1 chunks ahead.  A lane copies 16 bytes = 4 pixels of one channel;
+        // chunk layout in shared memory [32 channels][32 pixels], read back conflict-free with lane = pixel.
+        const bool res_async = !kFQ && prm.res_async != 0;
+        float* res_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes + 2 * prm.wcls_smem) +
+                       e * (kResDepth * kResChunkFloats);
+        struct { int tile, c, kb; bool live, pix_ok; const float* base; } cur = {0, 0, 0, false, false, nullptr};
+        int issue_slot = 0, cons_slot = 0;
+        auto cur_set_tile = [&](int t) {
+            cur.tile = t;
+            cur.c = 0;
+            cur.live = t < total_tiles;
+            if (cur.live) {
+                const int mt = prm.fd_ntiles.div(t), nt = t - mt * prm.n_tiles;
+                const int64_t m = (int64_t)mt * kBM + quad * 32 + 4 * (lane & 7);
+                cur.pix_ok = m < prm.M;
+                const int im = cur.pix_ok ? prm.fd_pq.div((int)m) : 0;
+                cur.kb = nt * BN + half * cols + (lane >> 3);
+                cur.base = ep.residual + ((int64_t)im * g.K + cur.kb) * PQ + (int)(m - (int64_t)im * PQ);
+            }
+        };
+        auto issue_one = [&]() {  // next chunk of the stream (if any); always one commit group per call
+            if (cur.live) {
+                float* dst = res_s + issue_slot * kResChunkFloats + (lane >> 3) * 32 + 4 * (lane & 7);
+                const float* src = cur.base + (int64_t)cur.c * 32 * PQ;
+                const int k = cur.kb + cur.c * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (cur.pix_ok && k + 4 * i < g.K) cp_async16(dst + i * 128, src + (int64_t)i * 4 * PQ);
+                if (++cur.c == (cols >> 5)) cur_set_tile(cur.tile + (int)gridDim.x);
+            }
+            cp_async_commit();
+            issue_slot = issue_slot == kResDepth - 1 ? 0 : issue_slot + 1;
+        };
+        if (res_async) {
+            cur_set_tile(blockIdx.x);
+#pragma unroll
+            for (int i = 0; i < kResDepth - 1; ++i) issue_one();
+        }
         int buf = 0, iter = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -683,7 +735,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int64_t o_off = o_base + (int64_t)cc * PQ;
                 const bool has_res = ep.residual != nullptr && !acc_out;
                 float rv[32];
-                if (has_res && row_ok) {
+                if (res_async) {
+                    cp_async_wait<kResDepth - 2>();   // this chunk has landed (only younger groups may still be in flight)
+                    __syncwarp();
+                    const float* rs = res_s + cons_slot * kResChunkFloats + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) rv[j] = rs[j * 32];
+                    issue_one();   // into the slot of the PREVIOUS chunk, which every lane finished reading before the sync above
+                    cons_slot = cons_slot == kResDepth - 1 ? 0 : cons_slot + 1;
+                } else if (has_res && row_ok) {
                     const float* rs = ep.residual + o_off;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -1047,8 +1107,15 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             prm.wcls_smem = nr * nc * BN * 4;
         }
     }
-    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem;
-    size_t ring_budget = (fq ? kSmemBudgetFq : kSmemBudget) - 1024 - tail;
+    // residual tail: stream the identity through per-warp cp.async rings when 16-byte pieces line up (4 pixels of one
+    // image and channel) and two operand stages still fit next to the 96 KB of rings
+    prm.res_async = 0;
+    if (!fq && !halo && ep.residual != nullptr && ep.out_kind == QB200_OUT_F32 && (g.P * g.Q) % 4 == 0 &&
+        reinterpret_cast<uintptr_t>(ep.residual) % 16 == 0 && prm.M < (1ll << 31) &&
+        kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq)
+        prm.res_async = 1;
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0);
+    size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail;
     const size_t xb = (size_t)kFqKC * kBM * 4;
     if (fq) {
         // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
@@ -1139,7 +1206,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                         1024 /*align*/ + tail;
     static thread_local bool smem_set = false;
     if (!smem_set) {
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         smem_set = true;
     }
