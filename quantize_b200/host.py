@@ -285,6 +285,23 @@ def _block_forward(self, x, handoff=None, next_conv=None):
     return out if next_conv is None else (out, None)
 
 
+def _resnet_forward_chained(self, x):
+    """torchvision ResNet._forward_impl with the int8 hand-off running through ALL residual blocks, also across stage
+    boundaries (the first conv of a down-sampling block consumes the previous stage's output like any other conv1;
+    its 1x1 stride-2 shortcut conv reads the fp32 tensor)."""
+    x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+    blocks = [b for stage in (self.layer1, self.layer2, self.layer3, self.layer4) for b in stage]
+    handoff = None
+    for i, blk in enumerate(blocks):
+        nxt = blocks[i + 1] if i + 1 < len(blocks) else None
+        if nxt is not None and getattr(blk, "chain", False) and getattr(nxt, "chain", False):
+            x, handoff = blk(x, handoff, nxt.conv1)
+        else:
+            x = blk(x, handoff)
+            handoff = None
+    return self.fc(torch.flatten(self.avgpool(x), 1))
+
+
 def _stage_forward(self, x):
     """nn.Sequential of residual blocks: block i's last conv also writes the int8 input of block i+1's conv1 (when that
     block has an identity shortcut, i.e. conv1 is the only quantizing consumer besides the fp32 residual path)."""
@@ -320,9 +337,13 @@ def fuse_resnet_blocks(model, chain=False, cross_block=False):
             m.chain = chain
             m.forward = types.MethodType(_block_forward, m)
     if chain and cross_block and isinstance(model, R.ResNet):
-        for stage in (model.layer1, model.layer2, model.layer3, model.layer4):
-            if all(hasattr(b, "chain") for b in stage):
-                stage.forward = types.MethodType(_stage_forward, stage)
+        stages = (model.layer1, model.layer2, model.layer3, model.layer4)
+        if all(hasattr(b, "chain") for stage in stages for b in stage):
+            model.forward = types.MethodType(_resnet_forward_chained, model)
+        else:
+            for stage in stages:
+                if all(hasattr(b, "chain") for b in stage):
+                    stage.forward = types.MethodType(_stage_forward, stage)
     if isinstance(model, R.ResNet) and isinstance(model.conv1, QuantConv2d):
         model.conv1.fuse_relu = True        # stem: conv1 -> (folded bn) -> relu -> maxpool
         model.relu = nn.Identity()
