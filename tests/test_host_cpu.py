@@ -113,3 +113,22 @@ def test_conv_specs_and_work_match_survey():
     assert not specs[0]["relu_input"] and all(s["relu_input"] for s in specs[1:])
     ops18, _ = models.conv_stack_work(models.conv_layer_specs("resnet18", 128))
     assert abs(ops18 / 128 / 1e9 - 3.6271) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet50"])
+def test_fused_and_chained_block_forwards_keep_the_network_function_on_cpu(name):
+    """host.fuse_resnet_blocks rewires the block / stage / network forwards (ReLU and residual add folded into the
+    convs, hand-off plumbing between blocks).  Without the engine (CPU, fake-quant mode) every branch must fall back to
+    the torch ops and give the same output as the untouched module graph."""
+    import copy
+    from quantize_b200 import models
+    torch.manual_seed(0)
+    model = models.build_quantized(name, 8, 8, seed=0)
+    host.calibrate(model, torch.randn(2, 3, 64, 64))
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        want = model(x)
+        for kw in (dict(), dict(chain=True), dict(chain=True, cross_block=True)):
+            fused = host.fuse_resnet_blocks(copy.deepcopy(model), **kw)
+            got = fused(x)
+            assert torch.equal(got, want), kw
