@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kThreads)
 act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C, int Cp, int HW,
                               const PadSpec ps, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                               const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ uint4 tile[kPix * (kCw / 16)];
     __shared__ int rowoff[kPix];
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
@@ -163,6 +165,8 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
                          int Cp, int HW, int sub, int W_in, int Q_out, int PQ_out, const PadSpec ps,
                          const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                          const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ uint4 tile[kPix * (kCw / 16)];
     __shared__ int rowoff[kPix];
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
@@ -223,6 +227,8 @@ __global__ void __launch_bounds__(256)
 act_quantize_im2col_kernel(const float* __restrict__ x, uint32_t* __restrict__ a_col, ConvGeom g, int Kwords,
                            const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                            const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ uint32_t patch[];  // [rows_in][Wp], Wp = W + 2*pad
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
     const int Wp = g.W + 2 * g.pad;
@@ -286,8 +292,8 @@ int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, cons
     const size_t smem = (size_t)((kIm2colRows - 1) * g.stride + g.R) * (g.W + 2 * g.pad) * sizeof(uint32_t);
     QB_REQUIRE(smem <= 48 * 1024, QB200_EUNSUPPORTED, "act_quantize_im2col: input row too wide");
     const int pblocks = (g.P + kIm2colRows - 1) / kIm2colRows;
-    act_quantize_im2col_kernel<<<(unsigned)(g.N * pblocks), 256, smem, st>>>(x, reinterpret_cast<uint32_t*>(a_col), g, Kcol / 4,
-                                                                         aq->scale, aq->zero, aq->qmin, aq->qmax);
+    QB_CUDA(launch_pdl(act_quantize_im2col_kernel, dim3((unsigned)(g.N * pblocks)), dim3(256), smem, st, x, reinterpret_cast<uint32_t*>(a_col), g, Kcol / 4,
+                                                                         aq->scale, aq->zero, aq->qmin, aq->qmax));
     QB_LAUNCH_CHECK();
     return 0;
 }
@@ -314,11 +320,11 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PadSpec ps{0, H, W};
     if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
-        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
-                                                                  aq->qmax);
+        QB_CUDA(launch_pdl(act_quantize_nhwc_vec4_kernel, dim3(grid), dim3(kThreads), 0, st, x, q_nhwc, total, C, Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
+                                                                  aq->qmax));
     else
-        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, ps, aq->scale, aq->zero,
-                                                             aq->qmin, aq->qmax);
+        QB_CUDA(launch_pdl(act_quantize_nhwc_kernel, dim3(grid), dim3(kThreads), 0, st, x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, ps, aq->scale, aq->zero,
+                                                             aq->qmin, aq->qmax));
     QB_LAUNCH_CHECK();
     return 0;
 }
@@ -333,8 +339,8 @@ int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb20
     QB_REQUIRE(g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1, QB200_EINVAL, "act_quantize_subsampled: not a strided 1x1 layer");
     const int64_t total = (int64_t)g.N * g.P * g.Q;
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
-    act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, g.H * g.W, g.stride, g.W, g.Q, g.P * g.Q,
-                                                         PadSpec{0, g.H, g.W}, aq->scale, aq->zero, aq->qmin, aq->qmax);
+    QB_CUDA(launch_pdl(act_quantize_nhwc_kernel, dim3(grid), dim3(kThreads), 0, st, x, q, total, g.C, g.Cp, g.H * g.W, g.stride, g.W, g.Q, g.P * g.Q,
+                                                         PadSpec{0, g.H, g.W}, aq->scale, aq->zero, aq->qmin, aq->qmax));
     QB_LAUNCH_CHECK();
     return 0;
 }
@@ -348,11 +354,11 @@ int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_ac
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
     const PadSpec ps{g.pad, g.H, g.W};
     if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
-        act_quantize_nhwc_vec4_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
-                                                                  aq->qmax);
+        QB_CUDA(launch_pdl(act_quantize_nhwc_vec4_kernel, dim3(grid), dim3(kThreads), 0, st, x, q, total, g.C, g.Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
+                                                                  aq->qmax));
     else
-        act_quantize_nhwc_kernel<<<grid, kThreads, 0, st>>>(x, q, total, g.C, g.Cp, HW, 1, g.W, g.W, HW, ps, aq->scale, aq->zero,
-                                                             aq->qmin, aq->qmax);
+        QB_CUDA(launch_pdl(act_quantize_nhwc_kernel, dim3(grid), dim3(kThreads), 0, st, x, q, total, g.C, g.Cp, HW, 1, g.W, g.W, HW, ps, aq->scale, aq->zero,
+                                                             aq->qmin, aq->qmax));
     QB_LAUNCH_CHECK();
     return 0;
 }
@@ -363,6 +369,8 @@ namespace {
 // left / right `pad` columns of the rows between.
 __global__ void __launch_bounds__(256)
 zero_pad_borders_kernel(uint4* __restrict__ q, int N, int H, int W, int pad, int chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     const int border = 2 * pad * Wp + 2 * pad * H;  // pad pixels per image
     const int64_t total = (int64_t)N * border * chunks;
@@ -394,7 +402,7 @@ int launch_zero_pad_borders(uint8_t* q, int N, int H, int W, int pad, int Cp, cu
     if (pad == 0 || N == 0) return 0;
     const int64_t total = (int64_t)N * (2 * pad * (W + 2 * pad) + 2 * pad * H) * (Cp / 16);
     const int blocks = (int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8);
-    zero_pad_borders_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<uint4*>(q), N, H, W, pad, Cp / 16);
+    QB_CUDA(launch_pdl(zero_pad_borders_kernel, dim3(blocks), dim3(256), 0, st, reinterpret_cast<uint4*>(q), N, H, W, pad, Cp / 16));
     QB_LAUNCH_CHECK();
     return 0;
 }

@@ -1,4 +1,5 @@
 // qb200 C-ABI: version, error string, launch counter.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace qb200 {
@@ -14,6 +15,14 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches += (uint64_t)n; }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 
 }  // namespace qb200
 

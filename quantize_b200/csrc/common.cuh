@@ -49,4 +49,31 @@ static inline size_t align_up_sz(size_t a, size_t b) { return (a + b - 1) / b * 
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+#ifdef __CUDACC__
+// Programmatic dependent launch: the engine's kernels run back to back on one stream (quantizer -> conv -> quantizer ...)
+// and each is short (20-400 us), so the launch latency and the prologue of kernel i+1 (barrier init, TMEM allocation,
+// tensor-map prefetch) are overlapped with the tail of kernel i.  Every kernel launched through launch_pdl executes
+// pdl_wait() before its first access to global memory that an earlier kernel may have written (and before its first
+// global write), and pdl_launch_dependents() as early as possible.  QB200_PDL=0 in the environment turns the attribute
+// off (A/B measurements).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 }  // namespace qb200

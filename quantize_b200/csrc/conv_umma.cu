@@ -354,6 +354,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
     tc_fence_before();
     __syncthreads();
+    // everything above touched only shared memory, TMEM and kernel parameters: it may overlap the previous kernel's tail
+    pdl_launch_dependents();
+    pdl_wait();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -1222,9 +1225,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(fp32 input) failed with CUresult %d", (int)r);
-        conv_umma_kernel<true><<<grid, kThreadsFq, smem, st>>>(tmap_a, tmap_b, prm, out);
+        QB_CUDA(launch_pdl(conv_umma_kernel<true>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a, tmap_b, prm, out));
     } else {
-        conv_umma_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap_b, prm, out);
+        QB_CUDA(launch_pdl(conv_umma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
     }
     QB_LAUNCH_CHECK();
     return 0;

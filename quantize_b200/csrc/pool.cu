@@ -26,6 +26,8 @@ template <int KT, int ST>
 __global__ void __launch_bounds__(kPoolThreads)
 maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int W, int P, int Q, int k_rt, int stride_rt, int pad,
                  int band_rows, int bands, int in_rows_alloc) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int k = KT ? KT : k_rt, stride = ST ? ST : stride_rt;
     extern __shared__ float tile[];
     const int plane = blockIdx.x / bands, band = blockIdx.x - plane * bands;
@@ -121,8 +123,8 @@ extern "C" int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, in
     QB_REQUIRE(planes * bands < (1ll << 31), QB200_EINVAL, "maxpool2d: too many blocks");
     auto launch = [&](auto kern) -> int {
         QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<(unsigned)(planes * bands), kPoolThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-            x, out, H, W, P, Q, kernel, stride, pad, band_rows, bands, in_rows);
+        QB_CUDA(launch_pdl(kern, dim3((unsigned)(planes * bands)), dim3(kPoolThreads), smem, static_cast<cudaStream_t>(stream),
+                           x, out, H, W, P, Q, kernel, stride, pad, band_rows, bands, in_rows));
         return 0;
     };
     if (kernel == 3 && stride == 2) { if (int rc = launch(maxpool2d_kernel<3, 2>)) return rc; }
