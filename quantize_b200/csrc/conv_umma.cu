@@ -302,7 +302,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kFQ>
+// kRes: the fused residual tail is compiled in.  It is a template parameter because its mere presence (ring state, 32 more
+// live registers per chunk) cost the plain kernel 6 % on output-heavy layers.
+template <bool kFQ, bool kRes>
 __global__ void __launch_bounds__(kFQ ? kThreadsFq : kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
@@ -452,6 +454,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait(&xfull[hs], hphase, prm.err_flag, 7);
                     const uint32_t halo_lo = xring16 + (uint32_t)hs * x16;
                     const uint32_t b16 = b_bytes >> 4;
+                    if (R == 3 && S == 3 && (n_mma == 2 || n_mma == 4) && (prm.tap_group == 9 || prm.tap_group == 3)) {
+                        // 3x3 kernels: the MMAs of one filter row (3 taps x n_mma k-slices) with compile-time offsets.
+                        // The generic loop below spent ~490 cycles per tap on loop bookkeeping and on moving operands to
+                        // uniform registers (ncu source page: 75 instructions per tap around 2 MMAs), and the issuing
+                        // warp — not the epilogue or memory — bounded these layers (64->64 3x3 @56x56: 104 -> 73 us).
+                        auto mma_row = [&](auto nm_tag, uint32_t a_row, uint32_t b_row, uint32_t first_acc) {
+                            constexpr int NM = decltype(nm_tag)::value;
+#pragma unroll
+                            for (int ss = 0; ss < 3; ++ss) {
+#pragma unroll
+                                for (int k = 0; k < NM; ++k)
+                                    umma_i8_lohi(tmem_d, a_row + (uint32_t)ss * kc16 + 2u * k, b_row + (uint32_t)ss * b16 + 2u * k,
+                                                 desc_hi, idesc, (ss | k) ? 1u : first_acc);
+                            }
+                        };
+                        const uint32_t a_row0 = halo_lo | lo_flag;
+                        const bool per_row = prm.tap_group == 3;   // one weight stage per filter row, else one per tile
+                        for (int rr = 0; rr < 3; ++rr) {
+                            if (rr == 0 || per_row) {
+                                mbar_wait(&full[stage], phase, prm.err_flag, 3);
+                                tc_fence_after();
+                            }
+                            if (lane == 0) {
+                                const uint32_t a_row = a_row0 + (uint32_t)rr * wp16;
+                                const uint32_t b_row = (stage_lo | lo_flag) + (per_row ? 0u : (uint32_t)(rr * 3) * b16);
+                                if (n_mma == 2) mma_row(std::integral_constant<int, 2>{}, a_row, b_row, accumulate);
+                                else mma_row(std::integral_constant<int, 4>{}, a_row, b_row, accumulate);
+                                if (per_row || rr == 2) umma_commit(&empty[stage]);
+                            }
+                            accumulate = 1;
+                            if (per_row || rr == 2) {
+                                stage_lo += stage16;
+                                if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
+                            }
+                        }
+                        if (lane == 0) umma_commit(&xempty[hs]);
+                        if (++hs == h_stages) { hs = 0; hphase ^= 1; }
+                        continue;
+                    }
                     int r = 0, s2 = 0;
                     uint32_t a_lo = halo_lo;   // tap (r, s): the halo rows shifted by r*Wp + s
                     for (int tap = 0; tap < R * S; tap += prm.tap_group) {
@@ -480,12 +521,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     mbar_wait<kFQ ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
                     tc_fence_after();
                     if (lane == 0) {
-                        for (int k = 0; k < n_mma; ++k) {
-                            umma_i8_lohi(tmem_d, (stage_lo + 2 * k) | lo_flag, (stage_lo + a16 + 2 * k) | lo_flag, desc_hi, idesc, accumulate);
-                            accumulate = 1;
+                        const uint32_t a0 = stage_lo | lo_flag, b0 = (stage_lo + a16) | lo_flag;
+                        if (n_mma == 4) {          // KC = 128
+                            umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
+                            umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);
+                            umma_i8_lohi(tmem_d, a0 + 4, b0 + 4, desc_hi, idesc, 1u);
+                            umma_i8_lohi(tmem_d, a0 + 6, b0 + 6, desc_hi, idesc, 1u);
+                        } else if (n_mma == 2) {   // KC = 64
+                            umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
+                            umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);
+                        } else {
+                            umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
                         }
                         umma_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
                     }
+                    accumulate = 1;
                     stage_lo += stage16;
                     if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
                 }
@@ -606,7 +656,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // loads).  Each warp therefore streams ITS chunks — in the order it will consume them, across tiles — through a
         // private cp.async ring, kResDepth - 1 chunks ahead.  A lane copies 16 bytes = 4 pixels of one channel;
         // chunk layout in shared memory [32 channels][32 pixels], read back conflict-free with lane = pixel.
-        const bool res_async = !kFQ && prm.res_async != 0;
+        const bool res_async = kRes && prm.res_async != 0;
         float* res_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes + 2 * prm.wcls_smem) +
                        e * (kResDepth * kResChunkFloats);
         struct { int tile, c, kb; bool live, pix_ok; const float* base; } cur = {0, 0, 0, false, false, nullptr};
@@ -736,7 +786,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // torch ops (conv result rounded, then one add, then max).  The residual values of the whole chunk are
                 // requested before the accumulator is read, so their latency overlaps the TMEM load.
                 const int64_t o_off = o_base + (int64_t)cc * PQ;
-                const bool has_res = ep.residual != nullptr && !acc_out;
+                const bool has_res = kRes && ep.residual != nullptr && !acc_out;
                 float rv[32];
                 if (res_async) {
                     cp_async_wait<kResDepth - 2>();   // this chunk has landed (only younger groups may still be in flight)
@@ -1023,6 +1073,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     const bool fq = x_fused != nullptr;
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
                "conv_umma: layer not eligible for the halo variant");
+    QB_REQUIRE(!(fq && ep.residual), QB200_EINVAL, "conv_umma: the fused-quantize kernel has no residual tail");
     if (fq) {
         QB_REQUIRE(umma_fused_quant_supported(g, x_fused) && gemm_rows == 0 && aq_fused && aq_fused->qmin && aq_fused->qmax,
                    QB200_EINVAL, "conv_umma: layer not eligible for the fused-quantize kernel");
@@ -1209,8 +1260,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                         1024 /*align*/ + tail;
     static thread_local bool smem_set = false;
     if (!smem_set) {
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         smem_set = true;
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
@@ -1225,9 +1277,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(fp32 input) failed with CUresult %d", (int)r);
-        QB_CUDA(launch_pdl(conv_umma_kernel<true>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a, tmap_b, prm, out));
+        QB_CUDA(launch_pdl(conv_umma_kernel<true, false>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a, tmap_b, prm, out));
     } else {
-        QB_CUDA(launch_pdl(conv_umma_kernel<false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        if (ep.residual != nullptr)
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        else
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
     }
     QB_LAUNCH_CHECK();
     return 0;
