@@ -304,7 +304,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // ---------------------------------------------------------------------------------------------
 // kRes: the fused residual tail is compiled in.  It is a template parameter because its mere presence (ring state, 32 more
 // live registers per chunk) cost the plain kernel 6 % on output-heavy layers.
-template <bool kFQ, bool kRes>
+// kQ8: the quantized hand-off (int8-out epilogue) is compiled in — same reason.
+template <bool kFQ, bool kRes, bool kQ8>
 __global__ void __launch_bounds__(kFQ ? kThreadsFq : kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
@@ -648,7 +649,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const EpilogueScalars es = load_epilogue_scalars(ep);
         const bool acc_out = ep.out_kind == QB200_OUT_ACC;
         QuantParams q8p = {};
-        if (!kFQ && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
+        if (kQ8 && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
         const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
         // ---- residual stream (fused tail) ----
         // The identity tensor is the largest read of a residual layer and a warp that loads one 32-channel chunk at a
@@ -812,7 +813,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (ep.relu) val = fmaxf(val, 0.f);
                     return val;
                 };
-                if constexpr (!kFQ) {
+                if constexpr (kQ8) {
                     if (ep.q8_out != nullptr) {
                         // Quantized hand-off: the chunk's 32 channels of this pixel, after the tail, go through the
                         // CONSUMER's activation quantizer and land as 32 contiguous bytes of its NHWC workspace.
@@ -1073,7 +1074,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     const bool fq = x_fused != nullptr;
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
                "conv_umma: layer not eligible for the halo variant");
-    QB_REQUIRE(!(fq && ep.residual), QB200_EINVAL, "conv_umma: the fused-quantize kernel has no residual tail");
+    QB_REQUIRE(!(fq && (ep.residual || ep.q8_out)), QB200_EINVAL, "conv_umma: the fused-quantize kernel has no residual / hand-off tail");
     if (fq) {
         QB_REQUIRE(umma_fused_quant_supported(g, x_fused) && gemm_rows == 0 && aq_fused && aq_fused->qmin && aq_fused->qmax,
                    QB200_EINVAL, "conv_umma: layer not eligible for the fused-quantize kernel");
@@ -1260,9 +1261,11 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                         1024 /*align*/ + tail;
     static thread_local bool smem_set = false;
     if (!smem_set) {
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
-        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         smem_set = true;
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
@@ -1277,12 +1280,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(fp32 input) failed with CUresult %d", (int)r);
-        QB_CUDA(launch_pdl(conv_umma_kernel<true, false>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a, tmap_b, prm, out));
+        QB_CUDA(launch_pdl(conv_umma_kernel<true, false, false>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a, tmap_b, prm, out));
     } else {
-        if (ep.residual != nullptr)
-            QB_CUDA(launch_pdl(conv_umma_kernel<false, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        const bool res = ep.residual != nullptr, q8 = ep.q8_out != nullptr;
+        if (res && q8)
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, true, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        else if (res)
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, true, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        else if (q8)
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, false, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
         else
-            QB_CUDA(launch_pdl(conv_umma_kernel<false, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, false, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
     }
     QB_LAUNCH_CHECK();
     return 0;
