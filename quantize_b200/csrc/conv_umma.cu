@@ -286,7 +286,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory"); }
+__device__ __forceinline__ void epi_barrier(int group) { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEpiWarps * 32) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (tcgen05): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
@@ -305,8 +305,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // kRes: the fused residual tail is compiled in.  It is a template parameter because its mere presence (ring state, 32 more
 // live registers per chunk) cost the plain kernel 6 % on output-heavy layers.
 // kQ8: the quantized hand-off (int8-out epilogue) is compiled in — same reason.
-template <bool kFQ, bool kRes, bool kQ8>
-__global__ void __launch_bounds__(kFQ ? kThreadsFq : kThreads, 1)
+// kGroups = 2: two groups of eight epilogue warps work on alternate tiles (int8-only hand-off layers: their epilogue is
+// instruction- and latency-bound — ~2 us per 128 x 64 tile with 2 warps per scheduler — so a second group doubles it).
+template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1>
+__global__ void __launch_bounds__(kFQ ? kThreadsFq : 64 + kGroups * kEpiWarps * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
@@ -639,10 +641,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else {
         // ===================== epilogue =====================
-        const int e = warp - 2;
+        const int grp = kGroups > 1 ? (warp - 2) >> 3 : 0;   // epilogue group: tiles grp, grp + kGroups, ... of this CTA
+        const int e = (warp - 2) & 7;
         const int quad = warp & 3;   // TMEM lane quadrant this warp may read
         const int half = e >> 2;     // which half of the tile's columns
-        const int et = threadIdx.x - 64;
+        const int et = (threadIdx.x - 64) & (kEpiWarps * 32 - 1);   // thread index inside the group
         const int row = quad * 32 + lane;
         const int PQ = g.P * g.Q;
         const EpilogueParams& ep = prm.ep;
@@ -650,6 +653,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const bool acc_out = ep.out_kind == QB200_OUT_ACC;
         QuantParams q8p = {};
         if (kQ8 && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
+        // int8-only output: relu(v) followed by the quantizer's clamp to [xlo, xhi] is one clamp to [max(xlo, 0), xhi]
+        // (a NaN ends at the lower bound either way), so the separate ReLU is dropped
+        const bool relu_folded = kQ8 && !kRes && ep.q8_out != nullptr && !ep.store_f32 && ep.relu != 0;
+        if (relu_folded) q8p.xlo = fmaxf(q8p.xlo, 0.f);
         const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
         // ---- residual stream (fused tail) ----
         // The identity tensor is the largest read of a residual layer and a warp that loads one 32-channel chunk at a
@@ -693,9 +700,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int i = 0; i < kResDepth - 1; ++i) issue_one();
         }
-        int buf = 0, iter = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const int acc_shift = prm.n_acc == 4 ? 2 : 1;
+        int iter = 0;
+        for (int tile = blockIdx.x + grp * (int)gridDim.x, it = grp; tile < total_tiles;
+             tile += kGroups * (int)gridDim.x, it += kGroups, ++iter) {
+            const int buf = it & (prm.n_acc - 1);                       // the MMA warp fills the buffers in tile order
+            const uint32_t acc_phase = (uint32_t)(it >> acc_shift) & 1u;
             const int m_tile = prm.fd_ntiles.div(tile);
             const int n_tile = tile - m_tile * prm.n_tiles;
             const int k_base = n_tile * BN;
@@ -735,7 +745,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     be[et] = beff;
                     br[et] = bias;
                 }
-                epi_barrier();
+                epi_barrier(grp);
             }
             bool row_ok;
             int img, pq;
@@ -810,7 +820,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const bool any_tail = has_res || ep.relu;
                 auto tail = [&](float val, int j) {
                     if (has_res) val = __fadd_rn(val, rv[j]);
-                    if (ep.relu) val = fmaxf(val, 0.f);
+                    if (ep.relu && !relu_folded) val = fmaxf(val, 0.f);
                     return val;
                 };
                 if constexpr (kQ8) {
@@ -856,9 +866,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (k_base + cc < ep.q8_cp) {
                             const int n_valid = g.K - (k_base + cc);  // channels of this chunk that exist (others stay 0)
                             uint32_t w[8];
-#pragma unroll
-                            for (int jj = 0; jj < 8; ++jj)
-                                w[jj] = quant_word(r[4 * jj], r[4 * jj + 1], r[4 * jj + 2], r[4 * jj + 3], q8p);
+                            quant_row<8>(r, w, q8p);
                             if (n_valid < 32) {
 #pragma unroll
                                 for (int jj = 0; jj < 8; ++jj) {
@@ -950,7 +958,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            if (++buf == prm.n_acc) { buf = 0; acc_phase ^= 1; }
         }
     }
 
@@ -1264,6 +1271,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         smem_set = true;
@@ -1287,6 +1295,8 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             QB_CUDA(launch_pdl(conv_umma_kernel<false, true, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
         else if (res)
             QB_CUDA(launch_pdl(conv_umma_kernel<false, true, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        else if (q8 && !ep.store_f32 && prm.n_tiles == 1)   // int8-only output, one channel tile: two epilogue groups
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, false, true, 2>, dim3(grid), dim3(64 + 2 * kEpiWarps * 32), smem, st, tmap_a, tmap_b, prm, out));
         else if (q8)
             QB_CUDA(launch_pdl(conv_umma_kernel<false, false, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
         else

@@ -1,6 +1,7 @@
 // Activation-quantizer arithmetic shared by the standalone quantizer kernels (actquant.cu) and the fused
 // quantizing producer of the 1x1 tensor-core kernel (conv_umma.cu).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 
 namespace qb200 {
@@ -9,7 +10,8 @@ struct QuantParams {
     float s, z, lo, hi;  // the reference's parameters
     float r;             // RN(1/s)
     float xlo, xhi;      // inputs outside [xlo, xhi] quantize to qmin / qmax whatever their value (2 steps of margin)
-    uint32_t lo4, hi4;   // qmin / qmax replicated into 4 bytes (valid when byte_clamp)
+    int ilo, ihi;        // qmin / qmax as integers (valid when byte_clamp)
+    int full_range;      // [qmin, qmax] == [0, 255]: the saturating pack is the whole clamp
     int byte_clamp;      // 0 <= qmin <= qmax <= 255, both integral, scale normal: the branch-free path applies
 };
 
@@ -27,9 +29,9 @@ __device__ __forceinline__ QuantParams load_params(const float* p_scale, const f
     // the division refinement below needs a normal positive scale with headroom and a bounded zero point
     const bool scale_ok = p.s > 1e-30f && p.s < 1e30f && fabsf(p.z) < 1048576.f;
     p.byte_clamp = (range_ok && scale_ok) ? 1 : 0;
-    const uint32_t l = (uint32_t)(int)fminf(fmaxf(p.lo, 0.f), 255.f), h = (uint32_t)(int)fminf(fmaxf(p.hi, 0.f), 255.f);
-    p.lo4 = l * 0x01010101u;
-    p.hi4 = h * 0x01010101u;
+    p.ilo = (int)fminf(fmaxf(p.lo, 0.f), 255.f);
+    p.ihi = (int)fminf(fmaxf(p.hi, 0.f), 255.f);
+    p.full_range = (p.byte_clamp && p.ilo == 0 && p.ihi == 255) ? 1 : 0;
     return p;
 }
 
@@ -93,12 +95,22 @@ __device__ __forceinline__ void quant_int2(float x0, float x1, const QuantParams
     i1 = (int)u1 - 0x4B400000;
 }
 
-// saturating pack of four integers to u8 (i0 in the low byte), then byte-wise clamp to [qmin, qmax]
+// saturating pack of four integers to u8 (i0 in the low byte) after the clamp to [qmin, qmax].  The byte-wise SIMD
+// min / max intrinsics are emulated on sm_100 (14 instructions per word — a third of the quantizer's issue slots), so
+// the clamp is done on the integers (2 instructions per value), and not at all for the common [0, 255] range where
+// the saturating pack already is the clamp.
+template <bool kFull>
 __device__ __forceinline__ uint32_t pack_clamp4(int i0, int i1, int i2, int i3, const QuantParams& p) {
+    if (!kFull) {
+        i0 = min(max(i0, p.ilo), p.ihi);
+        i1 = min(max(i1, p.ilo), p.ihi);
+        i2 = min(max(i2, p.ilo), p.ihi);
+        i3 = min(max(i3, p.ilo), p.ihi);
+    }
     uint32_t hi16, w;
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(i3), "r"(i2), "r"(0));
     asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(i1), "r"(i0), "r"(hi16));
-    return __vminu4(__vmaxu4(w, p.lo4), p.hi4);
+    return w;
 }
 
 // One output word = four channels of one pixel.
@@ -109,7 +121,29 @@ __device__ __forceinline__ uint32_t quant_word(float x0, float x1, float x2, flo
     int q0, q1, q2, q3;
     quant_int2(x0, x1, p, q0, q1);
     quant_int2(x2, x3, p, q2, q3);
-    return pack_clamp4(q0, q1, q2, q3, p);
+    return p.full_range ? pack_clamp4<true>(q0, q1, q2, q3, p) : pack_clamp4<false>(q0, q1, q2, q3, p);
+}
+
+// NW words from 4*NW consecutive channels of one pixel, the range / exactness switches hoisted out of the unrolled loop
+template <int NW>
+__device__ __forceinline__ void quant_row(const float (&r)[4 * NW], uint32_t (&w)[NW], const QuantParams& p) {
+    if (!p.byte_clamp) {
+#pragma unroll   // (a rolled loop would index r[] dynamically and push the caller's arrays into local memory)
+        for (int k = 0; k < NW; ++k) w[k] = quant_word_exact(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3], p.s, p.z, p.lo, p.hi);
+        return;
+    }
+    auto body = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            int q0, q1, q2, q3;
+            quant_int2(r[4 * k], r[4 * k + 1], p, q0, q1);
+            quant_int2(r[4 * k + 2], r[4 * k + 3], p, q2, q3);
+            w[k] = pack_clamp4<kFull>(q0, q1, q2, q3, p);
+        }
+    };
+    if (p.full_range) body(std::true_type{});
+    else body(std::false_type{});
 }
 
 // 4*NQ channels x four consecutive pixels (v[c] = the 4 pixels of channel c, as loaded) -> w[pixel][word]: NQ words
@@ -127,17 +161,22 @@ __device__ __forceinline__ void quant_tile(const float4 (&v)[4 * NQ], uint32_t (
         }
         return;
     }
+    auto body = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-    for (int k = 0; k < NQ; ++k) {
-        int i[4][4];  // [channel][pixel]
+        for (int k = 0; k < NQ; ++k) {
+            int i[4][4];  // [channel][pixel]
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            quant_int2(v[4 * k + c].x, v[4 * k + c].y, p, i[c][0], i[c][1]);
-            quant_int2(v[4 * k + c].z, v[4 * k + c].w, p, i[c][2], i[c][3]);
+            for (int c = 0; c < 4; ++c) {
+                quant_int2(v[4 * k + c].x, v[4 * k + c].y, p, i[c][0], i[c][1]);
+                quant_int2(v[4 * k + c].z, v[4 * k + c].w, p, i[c][2], i[c][3]);
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) w[px][k] = pack_clamp4<kFull>(i[0][px], i[1][px], i[2][px], i[3][px], p);
         }
-#pragma unroll
-        for (int px = 0; px < 4; ++px) w[px][k] = pack_clamp4(i[0][px], i[1][px], i[2][px], i[3][px], p);
-    }
+    };
+    if (p.full_range) body(std::true_type{});
+    else body(std::false_type{});
 }
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
