@@ -282,13 +282,92 @@ act_quantize_im2col_kernel(const float* __restrict__ x, uint32_t* __restrict__ a
     }
 }
 
+// Grouped rows (im2col_grouped: the 7x7 stem).  Same block shape; the input rows are quantized once into per-channel
+// byte planes plane[c][row][Wq] (column j = input column j - pad; zeros outside the image), and the 8 bytes of group
+// (c, r) of output pixel (p, q) are the window plane[c][p*stride + r][q*stride .. q*stride + 7]: three aligned words and
+// two funnel shifts.  Bytes C*R*8 .. Kcol-1 of a row are never written: their weights are zero and any byte times zero
+// is zero in integer arithmetic.
+__global__ void __launch_bounds__(256)
+act_quantize_im2col8_kernel(const float* __restrict__ x, uint8_t* __restrict__ a_col, ConvGeom g, int Kcol, int Wq,
+                            const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                            const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ uint32_t plane32[];  // [C][rows_in][Wq / 4] words
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int pblocks = (g.P + kIm2colRows - 1) / kIm2colRows;
+    const int n = blockIdx.x / pblocks, p0 = (blockIdx.x - n * pblocks) * kIm2colRows;
+    const int n_out = min(kIm2colRows, g.P - p0);
+    const int rows_max = (kIm2colRows - 1) * g.stride + g.R;
+    const int rows_in = (n_out - 1) * g.stride + g.R;
+    const int h0 = p0 * g.stride - g.pad;
+    const int HW = g.H * g.W, Ww = Wq >> 2;
+    // ---- quantize: one thread = 4 consecutive columns of one (channel, row) ----
+    for (int i = threadIdx.x; i < g.C * rows_in * Ww; i += blockDim.x) {
+        const int cr = i / Ww, jw = i - cr * Ww;
+        const int c = cr / rows_in, r = cr - c * rows_in;
+        const int ih = h0 + r, iw0 = jw * 4 - g.pad;
+        uint32_t word = 0;
+        if (ih >= 0 && ih < g.H && iw0 + 3 >= 0 && iw0 < g.W) {
+            const float* xr = x + ((int64_t)n * g.C + c) * HW + (int64_t)ih * g.W;
+            float a[4];
+            uint32_t keep = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const bool in = iw0 + b >= 0 && iw0 + b < g.W;
+                a[b] = in ? __ldg(xr + iw0 + b) : 0.f;
+                if (in) keep |= 0xFFu << (8 * b);
+            }
+            word = quant_word(a[0], a[1], a[2], a[3], p) & keep;
+        }
+        plane32[(c * rows_max + r) * Ww + jw] = word;
+    }
+    __syncthreads();
+    // ---- write: thread = one group index for a strided set of pixels ----
+    const int G = g.C * g.R, Gall = Kcol >> 3;           // real groups / 8-byte slots per row (the rest are written as 0:
+    const int per_iter = blockDim.x / Gall;              // whole 32-byte sectors, no read-modify-write in DRAM)
+    const int gi = threadIdx.x % Gall, qlane = threadIdx.x / Gall;
+    if (qlane < per_iter) {
+        const int c = gi / g.R, r = gi - c * g.R;
+        const bool real = gi < G;
+        for (int t = 0; t < n_out; ++t) {
+            uint8_t* orow = a_col + ((int64_t)n * g.P + p0 + t) * g.Q * Kcol + gi * 8;
+            const uint32_t* prow = plane32 + (real ? (c * rows_max + t * g.stride + r) * Ww : 0);
+#pragma unroll 4
+            for (int q = qlane; q < g.Q; q += per_iter) {
+                const int col = q * g.stride;
+                const uint32_t* w = prow + (col >> 2);
+                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                const int sh = (col & 3) * 8;
+                uint2 v;
+                v.x = real ? __funnelshift_r(w0, w1, sh) : 0u;
+                v.y = real ? __funnelshift_r(w1, w2, sh) : 0u;
+                *reinterpret_cast<uint2*>(orow + (int64_t)q * Kcol) = v;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
                                cudaStream_t st) {
     QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL,
                "act_quantize: activation quantizer parameters missing");
-    QB_REQUIRE(g.C <= 4 && g.groups == 1 && Kcol >= g.R * g.S * 4, QB200_EINVAL, "act_quantize_im2col: not a few-channel layer");
+    QB_REQUIRE(g.C <= 4 && g.groups == 1, QB200_EINVAL, "act_quantize_im2col: not a few-channel layer");
+    if (im2col_grouped(g.C, g.R, g.S)) {
+        QB_REQUIRE(Kcol == im2col8_row_bytes(g.C, g.R) && g.C * g.R <= 256, QB200_EINVAL, "act_quantize_im2col: bad row size");
+        // plane width: the last window starts at (Q-1)*stride and spans 8 bytes + 4 of slack for the third word
+        const int Wq = round_up_int(std::max(g.W + 2 * g.pad, (g.Q - 1) * g.stride + 12), 4);
+        const size_t smem8 = (size_t)g.C * ((kIm2colRows - 1) * g.stride + g.R) * Wq;
+        QB_REQUIRE(smem8 <= 48 * 1024, QB200_EUNSUPPORTED, "act_quantize_im2col: input row too wide");
+        const int pb = (g.P + kIm2colRows - 1) / kIm2colRows;
+        QB_CUDA(launch_pdl(act_quantize_im2col8_kernel, dim3((unsigned)(g.N * pb)), dim3(256), smem8, st, x, a_col, g, Kcol, Wq,
+                           aq->scale, aq->zero, aq->qmin, aq->qmax));
+        QB_LAUNCH_CHECK();
+        return 0;
+    }
+    QB_REQUIRE(Kcol >= g.R * g.S * 4, QB200_EINVAL, "act_quantize_im2col: bad row size");
     const size_t smem = (size_t)((kIm2colRows - 1) * g.stride + g.R) * (g.W + 2 * g.pad) * sizeof(uint32_t);
     QB_REQUIRE(smem <= 48 * 1024, QB200_EUNSUPPORTED, "act_quantize_im2col: input row too wide");
     const int pblocks = (g.P + kIm2colRows - 1) / kIm2colRows;

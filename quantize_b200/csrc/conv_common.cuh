@@ -30,6 +30,15 @@ static inline int im2col_row_bytes(int R, int S) {
     const int kq = R * S * 4;
     return kq > 64 ? (kq + 127) / 128 * 128 : (kq > 32 ? 64 : 32);
 }
+// Grouped rows for wide filters (the 7x7 stem): 8 bytes per (channel, filter row) = that row's S <= 8 taps of ONE channel
+// (bytes S..7 meet zero weights), i.e. a window of 8 consecutive quantized pixels: 3*7*8 = 168 -> 192 bytes per output
+// pixel instead of 49 words = 196 -> 256.  Used when it is the smaller of the two.
+static inline int im2col8_row_bytes(int C, int R) {
+    const int kq = C * R * 8;
+    return kq > 64 ? (kq + 63) / 64 * 64 : (kq > 32 ? 64 : 32);
+}
+static inline bool im2col_grouped(int C, int R, int S) { return S <= 8 && im2col8_row_bytes(C, R) < im2col_row_bytes(R, S); }
+static inline int im2col_kcol(int C, int R, int S) { return im2col_grouped(C, R, S) ? im2col8_row_bytes(C, R) : im2col_row_bytes(R, S); }
 PreparedLayout prepared_layout(const qb200_conv_shape& s);
 int validate_shape(const qb200_conv_shape* s);
 

@@ -22,7 +22,7 @@ PreparedLayout prepared_layout(const qb200_conv_shape& s) {
     L.Kcol = 0;
     L.wcol_off = L.total;
     if (uses_im2col_rows(s)) {
-        L.Kcol = im2col_row_bytes(s.R, s.S);
+        L.Kcol = im2col_kcol(s.C, s.R, s.S);
         L.total = L.wcol_off + align_up_sz((size_t)s.K * L.Kcol, 256);
     }
     L.tapKC = 0;
@@ -74,14 +74,21 @@ __global__ void unpack_weights_kernel(const uint8_t* __restrict__ packed, uint8_
 }
 
 // im2col weight rows: byte (r*S + s)*4 + c of row k = wq[k][r][s][c], zero elsewhere
+// grouped: byte ((c*R + r)*8 + s) of row k = wq[k][r][s][c], zero elsewhere (im2col_grouped, conv_common.cuh)
 __global__ void im2col_weights_kernel(const uint8_t* __restrict__ wq, uint8_t* __restrict__ wcol, int K, int C, int R, int S,
-                                      int Cgp, int Kcol) {
+                                      int Cgp, int Kcol, int grouped) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)K * Kcol) return;
     const int k = (int)(i / Kcol), b = (int)(i % Kcol);
-    const int tap = b >> 2, c = b & 3;
     uint8_t v = 0;
-    if (tap < R * S && c < C) v = wq[((int64_t)k * R * S + tap) * Cgp + c];
+    if (grouped) {
+        const int gi = b >> 3, s = b & 7;
+        const int c = gi / R, r = gi - c * R;
+        if (c < C && s < S) v = wq[((int64_t)k * R * S + r * S + s) * Cgp + c];
+    } else {
+        const int tap = b >> 2, c = b & 3;
+        if (tap < R * S && c < C) v = wq[((int64_t)k * R * S + tap) * Cgp + c];
+    }
     wcol[i] = v;
 }
 
@@ -152,7 +159,7 @@ size_t qb200_conv_workspace_bytes(const qb200_conv_shape* s) {
     size_t bytes = (size_t)s->N * (s->H + 2 * s->pad) * (s->W + 2 * s->pad) * qb200_padded_channels(s->C);
     if (uses_im2col_rows(*s)) {
         const size_t P = (s->H + 2 * s->pad - s->R) / s->stride + 1, Q = (s->W + 2 * s->pad - s->S) / s->stride + 1;
-        const size_t col = (size_t)s->N * P * Q * im2col_row_bytes(s->R, s->S);
+        const size_t col = (size_t)s->N * P * Q * im2col_kcol(s->C, s->R, s->S);
         if (col > bytes) bytes = col;
     }
     return align_up_sz(bytes, 256);
@@ -182,7 +189,7 @@ int qb200_conv_prepare_weights(const qb200_conv_shape* s, const uint8_t* w_packe
     }
     if (L.Kcol) {
         im2col_weights_kernel<<<(unsigned)ceil_div64((int64_t)s->K * L.Kcol, 256), 256, 0, st>>>(
-            wq, wq + L.wcol_off, s->K, s->C, s->R, s->S, L.Cgp, L.Kcol);
+            wq, wq + L.wcol_off, s->K, s->C, s->R, s->S, L.Cgp, L.Kcol, im2col_grouped(s->C, s->R, s->S) ? 1 : 0);
         QB_LAUNCH_CHECK();
     }
     return 0;
