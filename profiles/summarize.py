@@ -28,7 +28,7 @@ def rows_of(path):
 
 def short(name):
     for key in ("conv_umma_kernel<1>", "conv_umma_kernel<0>", "act_quantize_nhwc_vec4_kernel",
-                "act_quantize_nhwc_kernel", "act_quantize_im2col_kernel", "zero_pad_borders_kernel", "maxpool2d_kernel"):
+                "act_quantize_nhwc_kernel", "act_quantize_im2col8_kernel", "act_quantize_im2col_kernel", "zero_pad_borders_kernel", "maxpool2d_kernel"):
         if key in name:
             return key
     return name[:60]
