@@ -45,7 +45,13 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", default="", help="debug: comma-separated layer indices to run")
     ap.add_argument("--per-layer", action="store_true", help="also print a per-layer table to stderr")
-    return ap.parse_args()
+    ap.add_argument("--w-bits", type=int, default=8, help="weight bits (BASELINE headline: 8)")
+    ap.add_argument("--a-bits", type=int, default=8, help="activation bits (BASELINE headline: 8)")
+    ap.add_argument("--sweep-out", default="", help="write the per-unique-shape layer sweep (SURVEY 8d config 5) as markdown")
+    a = ap.parse_args()
+    global W_BITS, A_BITS
+    W_BITS, A_BITS = a.w_bits, a.a_bits
+    return a
 
 
 def measured_peaks():
@@ -136,7 +142,8 @@ def run_reference(args):
     sample = 8
     ips, sec, cores = cpu_fakequant_stack(args.model, sample, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "ResNet-50 W8A8 images/sec", "value": round(ips, 3), "unit": "images/s",
+        "impl": "reference", "metric": ("ResNet-50 W8A8 images/sec" if (args.model, W_BITS, A_BITS) == ("resnet50", 8, 8)
+                       else f"{args.model} W{W_BITS}A{A_BITS} images/sec"), "value": round(ips, 3), "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.model} conv stack (53 convs) W{W_BITS}A{A_BITS} fake-quant on host CPU, "
@@ -153,6 +160,15 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # this engine
 # ---------------------------------------------------------------------------------------------------
+def im2col_kcol(C, R):
+    """bytes per materialised im2col row of a few-channel layer (csrc/conv_common.cuh: im2col_kcol)"""
+    kq = R * R * 4
+    words = (kq + 127) // 128 * 128 if kq > 64 else (64 if kq > 32 else 32)
+    k8 = C * R * 8
+    grouped = (k8 + 63) // 64 * 64 if k8 > 64 else (64 if k8 > 32 else 32)
+    return grouped if (R <= 8 and grouped < words) else words
+
+
 class ConvStack:
     """per-layer device operands for the C-ABI hot path"""
 
@@ -170,7 +186,8 @@ class ConvStack:
             if s["relu_input"]:
                 x.relu_()
             cg = s["C"] // s["groups"]
-            qw = torch.randint(-127, 128, (s["K"], cg, s["R"], s["R"]), generator=g, device=device).float()
+            wmax = (1 << (W_BITS - 1)) - 1                       # symmetric signed weights (range/minmax.py:123-135)
+            qw = torch.randint(-wmax, wmax + 1, (s["K"], cg, s["R"], s["R"]), generator=g, device=device).float()
             packed, des = qe.tpack(qw, W_BITS, True)             # reference format (tpack.cu:203-255)
             shape = capi.conv_shape(s["N"], s["C"], s["H"], s["W"], s["K"], cg, s["R"], s["R"], s["stride"], s["pad"],
                                     W_BITS, 1)
@@ -199,7 +216,7 @@ class ConvStack:
                 conv_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + w_bytes + 4 * s["N"] * s["K"] * P * Q
                 quant_bytes = 0
             elif s["C"] <= 4 and s["R"] > 1:   # quantizer writes im2col rows [N*P*Q][Kcol]; the conv is a GEMM over them
-                kcol = (s["R"] * s["R"] * 4 + 127) // 128 * 128 if s["R"] * s["R"] * 4 > 64 else (64 if s["R"] * s["R"] * 4 > 32 else 32)
+                kcol = im2col_kcol(s["C"], s["R"])
                 conv_bytes = s["N"] * P * Q * kcol + s["K"] * kcol + 12 * s["K"] + 4 * s["N"] * s["K"] * P * Q
                 quant_bytes = 4 * s["N"] * s["C"] * s["H"] * s["W"] + s["N"] * P * Q * kcol
             else:        # quantizer kernel (fp32 in, u8 out) + conv kernel (u8 in, fp32 out)
@@ -351,6 +368,37 @@ def run_b200(args):
                   f"quant {quant_ms[i]*1e3:7.1f} us {l['quant_bytes']/max(quant_ms[i],1e-9)/1e6:6.0f} GB/s | conv {conv_ms[i]*1e3:7.1f} us "
                   f"{l['conv_bytes']/conv_ms[i]/1e6:6.0f} GB/s {l['ops']/conv_ms[i]/1e9:6.0f} TOPS", file=sys.stderr)
 
+    if args.sweep_out and rank == 0:
+        # per unique layer shape: time of the fused op (quantizer + conv), its contract bytes / ops, and how close it is
+        # to its own roofline bound max(t_hbm, t_tensor)  (config 5)
+        groups = {}
+        for i, l in enumerate(stack.layers):
+            sp = l["spec"]
+            key = (sp["C"], sp["K"], sp["R"], sp["stride"], sp["H"], sp.get("groups", 1))
+            g_ = groups.setdefault(key, {"n": 0, "t": 0.0, "ops": l["ops"], "single": l["single"], "spec": sp})
+            g_["n"] += 1
+            g_["t"] += (0.0 if l["single"] else quant_ms[i]) + conv_ms[i]
+        with open(args.sweep_out, "w") as f:
+            f.write(f"# layer sweep: {args.model} W{W_BITS}A{A_BITS}, {args.batch} images, 1 x B200 — fused op per unique shape\n\n")
+            f.write("bytes = the op contract (fp32 in + fp32 out + packed weights + 12 B per output channel); bound = max(bytes / "
+                    f"{hbm_peak:.0f} GB/s, ops / {INT8_PEAK_TOPS} TOPS); `frac` = bound / measured time.\n\n")
+            f.write("| count | C->K | k | s | H | groups | kernels | us | GB/s (contract) | TOPS | % int8 spec | bound | frac of bound |\n")
+            f.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+            tot_t = tot_b = 0.0
+            for key, g_ in groups.items():
+                sp = g_["spec"]
+                t_us = g_["t"] / g_["n"] * 1e3
+                one = models.conv_stack_work([sp], W_BITS)
+                ops, byts = one[0], one[1]
+                t_hbm, t_tc = byts / (hbm_peak * 1e9) * 1e6, ops / (INT8_PEAK_TOPS * 1e12) * 1e6
+                bound = max(t_hbm, t_tc)
+                tot_t += g_["t"] * 1e3
+                tot_b += bound * g_["n"]
+                f.write(f"| {g_['n']} | {sp['C']}->{sp['K']} | {sp['R']} | {sp['stride']} | {sp['H']} | {sp.get('groups', 1)} | "
+                        f"{1 if g_['single'] else 2} | {t_us:.1f} | {byts / t_us / 1e3:.0f} | {ops / t_us / 1e6:.0f} | "
+                        f"{100 * ops / t_us / 1e6 / INT8_PEAK_TOPS:.1f} | {'hbm' if t_hbm >= t_tc else 'tensor'} | {bound / t_us:.2f} |\n")
+            f.write(f"\nwhole stack: {tot_t:.0f} us measured, {tot_b:.0f} us at the per-layer bounds = {tot_b / tot_t:.2f}\n")
+
     # ---- end to end through the public op API: host images -> logits on host ----------------------------
     e2e = None
     if not args.no_e2e and not args.layers:
@@ -420,7 +468,8 @@ def run_b200(args):
 
     if rank == 0:
         line = {
-            "metric": "ResNet-50 W8A8 images/sec", "value": round(value, 1), "unit": "images/s", "n_gpus": n_gpus,
+            "metric": ("ResNet-50 W8A8 images/sec" if (args.model, W_BITS, A_BITS) == ("resnet50", 8, 8)
+                       else f"{args.model} W{W_BITS}A{A_BITS} images/sec"), "value": round(value, 1), "unit": "images/s", "n_gpus": n_gpus,
             "steps": K, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8 x s8 -> s32 (fp32 dequant)", "data": "synthetic",
             "config": {"workload": f"{args.model} conv stack: {nl} convs via quantconv2d_float_input fused path "

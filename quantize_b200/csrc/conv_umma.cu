@@ -771,7 +771,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
             // without a class table, a warp with any border pixel computes the window form for all its lanes
             const bool warp_interior = __all_sync(0xffffffffu, interior || !row_ok);
-            const bool full_n = k_base + BN <= g.K;
             // this pixel's row of window sums: its class in the shared table, else the full-window sums
             const float* wrow = be;
             if (use_cls) {
@@ -812,6 +811,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         rv[j] = (k_base + cc + j < g.K) ? __ldg(rs + (int64_t)j * PQ) : 0.f;
+                }
+                // channel raggedness is handled per 32-column chunk: chunks past K are skipped (unless the hand-off must
+                // zero the consumer's padded channels), only a partially valid chunk takes the per-element path
+                const bool full_n = k_base + cc + 32 <= g.K;
+                if (k_base + cc >= g.K) {
+                    bool skip = true;
+                    if constexpr (kQ8) skip = ep.q8_out == nullptr || k_base + cc >= ep.q8_cp;
+                    if (skip) continue;
                 }
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
