@@ -22,7 +22,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libqb200.so")
 EXT = os.path.join(HERE, "quant_engine.so")
 
-CU_SOURCES = ["common.cu", "pack.cu", "actquant.cu", "wprep.cu", "conv_direct.cu", "conv_umma.cu", "conv_api.cu", "pool.cu"]
+CU_SOURCES = ["common.cu", "pack.cu", "actquant.cu", "wprep.cu", "conv_direct.cu", "conv_umma.cu", "conv_dw.cu", "conv_api.cu", "pool.cu"]
 HEADERS = ["common.cuh", "conv_common.cuh", "quant_math.cuh", os.path.join(ROOT, "include", "qb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

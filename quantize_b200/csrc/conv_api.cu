@@ -15,7 +15,11 @@ int resolve_algo(const ConvGeom& g) {
 }
 
 // 1x1 / stride-1 layers: the quantizer runs inside the tensor-core kernel's producer warps (one kernel, no workspace)
+// depthwise layers: one fused CUDA-core kernel (product default; the explicit algo settings keep the two-kernel paths)
+bool dw_single_kernel(const ConvGeom& g) { return g_conv_algo == QB200_ALGO_AUTO && dw_fused_supported(g); }
+
 bool single_kernel(const ConvGeom& g, const float* x) {
+    if (dw_single_kernel(g)) return true;
     if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || resolve_algo(g) != QB200_ALGO_UMMA) return false;
     if (!umma_fused_quant_supported(g, x)) return false;
     return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_fused_quant_profitable(g);
@@ -103,6 +107,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
         }
         ep.store_f32 = out != nullptr;
     }
+    if (x_fused && dw_single_kernel(g)) return launch_conv_dw_fused(g, x_fused, wq, ep, aq, out, st);
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
@@ -181,7 +186,10 @@ int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const 
     QB_REQUIRE(x != nullptr, QB200_EINVAL, "conv: null input");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // (a residual tail needs 32 more live registers in the epilogue than the 608-thread fused-quantize kernel has)
-    if (single_kernel(make_geom(*s), x) && !(tail && (tail->residual || tail->next_shape)))
+    const qb200::ConvGeom g0 = make_geom(*s);
+    if (dw_single_kernel(g0) && !(tail && tail->next_shape))   // (the depthwise kernel has the residual / ReLU tail)
+        return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x, tail);
+    if (single_kernel(g0, x) && !dw_single_kernel(g0) && !(tail && (tail->residual || tail->next_shape)))
         return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x, tail);
     if (int rc = quantize_input(s, x, aq, static_cast<uint8_t*>(workspace), st)) return rc;
     return run_conv(s, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st,

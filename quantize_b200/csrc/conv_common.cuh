@@ -156,6 +156,10 @@ static inline ConvGeom subsampled_geom(ConvGeom g) {
 int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
                                cudaStream_t st);
 bool umma_supported(const ConvGeom& g);
+// depthwise layers (groups == C, Cg == 1): quantizer + stencil + dequant in one CUDA-core kernel (conv_dw.cu)
+bool dw_fused_supported(const ConvGeom& g);
+int launch_conv_dw_fused(const ConvGeom& g, const float* x, const uint8_t* wq, const EpilogueParams& ep,
+                         const qb200_act_quant* aq, void* out, cudaStream_t st);
 int watchdog_code();
 
 }  // namespace qb200

@@ -307,7 +307,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // kQ8: the quantized hand-off (int8-out epilogue) is compiled in — same reason.
 // kGroups = 2: two groups of eight epilogue warps work on alternate tiles (int8-only hand-off layers: their epilogue is
 // instruction- and latency-bound — ~2 us per 128 x 64 tile with 2 warps per scheduler — so a second group doubles it).
-template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1>
+// kRagged: K is not a multiple of the channel tile; raggedness is then resolved per 32-column chunk (chunks past K are
+// skipped, only a partially valid chunk takes the per-element path).  A separate instantiation because the per-chunk
+// checks cost the common kernels 10 % on output-heavy layers (register pressure in the epilogue).
+template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1, bool kRagged = false>
 __global__ void __launch_bounds__(kFQ ? kThreadsFq : 64 + kGroups * kEpiWarps * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
@@ -771,6 +774,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
             // without a class table, a warp with any border pixel computes the window form for all its lanes
             const bool warp_interior = __all_sync(0xffffffffu, interior || !row_ok);
+            const bool full_n = k_base + BN <= g.K;
             // this pixel's row of window sums: its class in the shared table, else the full-window sums
             const float* wrow = be;
             if (use_cls) {
@@ -812,13 +816,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int j = 0; j < 32; ++j)
                         rv[j] = (k_base + cc + j < g.K) ? __ldg(rs + (int64_t)j * PQ) : 0.f;
                 }
-                // channel raggedness is handled per 32-column chunk: chunks past K are skipped (unless the hand-off must
-                // zero the consumer's padded channels), only a partially valid chunk takes the per-element path
-                const bool full_n = k_base + cc + 32 <= g.K;
-                if (k_base + cc >= g.K) {
-                    bool skip = true;
-                    if constexpr (kQ8) skip = ep.q8_out == nullptr || k_base + cc >= ep.q8_cp;
-                    if (skip) continue;
+                bool full_c = full_n;
+                if constexpr (kRagged) {
+                    full_c = k_base + cc + 32 <= g.K;
+                    if (k_base + cc >= g.K) continue;
                 }
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
@@ -889,7 +890,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         continue;
                     }
                 }
-                if (!acc_out && full_n && uniform_ok) {
+                if (!acc_out && full_c && uniform_ok) {
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
                     // kTail is a compile-time switch so that the plain op pays nothing for the optional fused tail.
@@ -1276,6 +1277,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     static thread_local bool smem_set = false;
     if (!smem_set) {
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
@@ -1306,6 +1308,8 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             QB_CUDA(launch_pdl(conv_umma_kernel<false, false, true, 2>, dim3(grid), dim3(64 + 2 * kEpiWarps * 32), smem, st, tmap_a, tmap_b, prm, out));
         else if (q8)
             QB_CUDA(launch_pdl(conv_umma_kernel<false, false, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
+        else if (g.K % BN != 0)   // ragged channel count (MobileNet-style 24 / 96 / 144 ... channels)
+            QB_CUDA(launch_pdl(conv_umma_kernel<false, false, false, 1, true>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
         else
             QB_CUDA(launch_pdl(conv_umma_kernel<false, false, false>, dim3(grid), dim3(kThreads), smem, st, tmap_a, tmap_b, prm, out));
     }
