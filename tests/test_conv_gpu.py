@@ -3,6 +3,8 @@
 Bar (BASELINE.json north_star): integer results bit-exact (quantized activations, int32 accumulators);
 dequantized fp32 outputs within 1e-3 relative.
 """
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -191,6 +193,31 @@ def test_auto_dispatch_matches():
     a0, o0 = run_case(c, capi.ALGO_AUTO)
     a1, o1 = run_case(c, capi.ALGO_DIRECT)
     assert torch.equal(a0, a1) and torch.equal(o0, o1)        # same epilogue arithmetic -> identical floats
+
+
+DEPTHWISE = [
+    (2, 32, 17, 19, 32, 3, 1, 1, 32, 8, 8),     # MobileNetV2-style 3x3, ragged plane
+    (3, 24, 15, 15, 24, 3, 2, 1, 24, 4, 8),     # stride 2, W4A8
+    (1, 16, 9, 9, 32, 3, 1, 1, 16, 8, 8),       # channel multiplier 2
+    (2, 8, 11, 11, 8, 5, 1, 2, 8, 8, 4),        # 5x5 (run-time loops), A4
+    (2, 96, 112, 112, 96, 3, 2, 1, 96, 4, 8),   # MobileNetV2 block 2 depthwise at its real spatial size
+    (2, 960, 7, 7, 960, 3, 1, 1, 960, 4, 8),    # the 7x7 tail
+]
+
+
+@pytest.mark.parametrize("cfg", DEPTHWISE, ids=lambda c: "N{}C{}H{}W{}K{}R{}s{}p{}g{}w{}a{}".format(*c))
+def test_depthwise_fused_kernel(cfg):
+    """groups == C layers run as ONE fused kernel (quantize + stencil + dequant, conv_dw.cu) by default: accumulators
+    bit-exact vs the oracle, fp32 within 1e-3, and identical floats to the two-kernel CUDA-core path."""
+    N, C, H, W, K, R, stride, pad, groups, wb, ab = cfg
+    c = random_conv_case(sum(cfg), N, C, H, W, K, R, stride, pad, groups, wb, ab)
+    assert capi.lib().qb200_conv_is_single_kernel(ctypes.byref(c["shape"]), None) == 1
+    acc, out = run_case(c, capi.ALGO_AUTO)
+    _, acc_ref, out_ref = oracle_case(c)
+    assert np.array_equal(acc.cpu().numpy(), acc_ref)
+    assert_close_1e3(out.cpu().numpy(), out_ref)
+    acc_d, out_d = run_case(c, capi.ALGO_DIRECT)
+    assert torch.equal(acc, acc_d) and torch.equal(out, out_d)
 
 
 # ---------------------------------------------------------------------------------------------------
