@@ -40,60 +40,141 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
     const int ih0 = oh0 * g.stride - g.pad, iw0 = -g.pad;
     const int taps = g.R * g.S;
     const int mult = g.K / g.groups;                      // output channels per input channel (Cg == 1)
-    int* wsm = reinterpret_cast<int*>(patch + (((size_t)CH * in_h * in_w_alloc + 15) & ~(size_t)15));   // [CH][taps]
+    // shared memory after the patch: the filters [CH][taps] and, for KS kernels, the in-bounds weight sums of the 16
+    // window classes [CH][16]: class = (first row missing) | (last row missing) << 1 | (first column missing) << 2 |
+    // (last column missing) << 3  (KS <= 3 with pad <= 1: at most one row / column is missing on each side)
+    int* wsm = reinterpret_cast<int*>(patch + (((size_t)CH * in_h * in_w_alloc + 15) & ~(size_t)15));
+    int* wcls = wsm + CH * taps;
     for (int i = threadIdx.x; i < nch * taps; i += kDwThreads) {
         const uint8_t b = wq[((int64_t)k0 * taps + i) * g.Cgp];
         wsm[i] = kSignedW ? (int)(int8_t)b : (int)b;
     }
+    const bool cls_ok = KS == 3 && g.pad <= 1;            // the class table describes every window
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- load + quantize: a warp takes (channel, input row) pairs, lanes run along the row ----
-    for (int pr = warp; pr < nch * in_h; pr += kDwWarps) {
-        const int ch = pr / in_h, r = pr - ch * in_h;
-        const int ih = ih0 + r;
-        const int c = (k0 + ch) / mult;
-        uint8_t* prow = patch + ((size_t)ch * in_h + r) * in_w_alloc;
-        const bool rok = ih >= 0 && ih < g.H;
-        const float* xr = x + (((int64_t)n * g.C + c) * g.H + (rok ? ih : 0)) * g.W;
-        for (int col = lane; col < in_w; col += 32) {
-            const int iw = iw0 + col;
-            uint8_t q = 0;
-            if (rok && iw >= 0 && iw < g.W) {
-                const float v = __ldg(xr + iw);
-                if (p.byte_clamp) q = (uint8_t)min(max(quant_int(v, p), p.ilo), p.ihi);
-                else q = (uint8_t)(quant_word_exact(v, 0.f, 0.f, 0.f, p.s, p.z, p.lo, p.hi) & 0xFFu);
+    // narrow planes (Q < 32: 14x14, 7x7): lanes run over the flattened (row, column) index of a channel's band instead,
+    // so that all 32 lanes work; the division by the row length is a multiply-shift (exact for indices < 1024, divisors < 64)
+    const bool flat = g.Q < 32 && in_h * in_w < 1024;
+    const uint32_t magic_in = (65536u + (uint32_t)in_w - 1u) / (uint32_t)in_w, magic_q = (65536u + (uint32_t)g.Q - 1u) / (uint32_t)g.Q;
+    auto quant1 = [&](float v) -> uint8_t {
+        if (p.byte_clamp) return (uint8_t)min(max(quant_int(v, p), p.ilo), p.ihi);
+        return (uint8_t)(quant_word_exact(v, 0.f, 0.f, 0.f, p.s, p.z, p.lo, p.hi) & 0xFFu);
+    };
+    // ---- load + quantize.  All loads of a pass are issued before the first value is used (a load -> quantize -> store
+    //      chain per element left one HBM round trip per element on the critical path of every warp). ----
+    if (flat) {
+        for (int ch = warp; ch < nch; ch += kDwWarps) {
+            const int c = (k0 + ch) / mult;
+            const float* xc = x + ((int64_t)n * g.C + c) * g.H * g.W;
+            uint8_t* pch = patch + (size_t)ch * in_h * in_w_alloc;
+            for (int i0 = 0; i0 < in_h * in_w; i0 += 128) {
+                float v[4];
+                int off[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u * 32 + lane;
+                    const int r = (int)(((uint32_t)i * magic_in) >> 16), col = i - r * in_w;
+                    const int ih = ih0 + r, iw = iw0 + col;
+                    const bool in = i < in_h * in_w && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                    off[u] = i < in_h * in_w ? r * in_w_alloc + col : -1;
+                    v[u] = in ? __ldg(xc + ih * g.W + iw) : __int_as_float(0x7fc00000);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (off[u] >= 0) pch[off[u]] = (v[u] == v[u]) ? quant1(v[u]) : (uint8_t)0;   // NaN marks "outside"
             }
-            prow[col] = q;
+        }
+    } else {
+        for (int pr = warp; pr < nch * in_h; pr += kDwWarps) {
+            const int ch = pr / in_h, r = pr - ch * in_h;
+            const int ih = ih0 + r;
+            const int c = (k0 + ch) / mult;
+            uint8_t* prow = patch + ((size_t)ch * in_h + r) * in_w_alloc;
+            const bool rok = ih >= 0 && ih < g.H;
+            const float* xr = x + (((int64_t)n * g.C + c) * g.H + (rok ? ih : 0)) * g.W;
+            for (int c0 = 0; c0 < in_w; c0 += 128) {
+                float v[4];
+                bool in[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col = c0 + u * 32 + lane, iw = iw0 + col;
+                    in[u] = rok && col < in_w && iw >= 0 && iw < g.W;
+                    v[u] = in[u] ? __ldg(xr + iw) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int col = c0 + u * 32 + lane;
+                    if (col < in_w) prow[col] = in[u] ? quant1(v[u]) : (uint8_t)0;
+                }
+            }
+        }
+    }
+    if (cls_ok) {
+        for (int i = threadIdx.x; i < nch * 16; i += kDwThreads) {
+            const int ch = i >> 4, cls = i & 15;
+            const int r_lo = cls & 1, r_hi = 3 - ((cls >> 1) & 1), c_lo = (cls >> 2) & 1, c_hi = 3 - ((cls >> 3) & 1);
+            int sum = 0;
+            for (int r = r_lo; r < r_hi; ++r)
+                for (int s2 = c_lo; s2 < c_hi; ++s2) {
+                    const uint8_t b = wq[((int64_t)(k0 + ch) * taps + r * 3 + s2) * g.Cgp];
+                    sum += kSignedW ? (int)(int8_t)b : (int)b;
+                }
+            wcls[i] = sum;
         }
     }
     __syncthreads();
 
-    // ---- stencil + dequant: a warp takes (channel, output row) pairs, lanes run along the row ----
+    // ---- stencil + dequant: a warp takes (channel, output row) pairs (or whole channel bands when `flat`) ----
     const EpilogueScalars es = load_epilogue_scalars(ep);
-    for (int pr = warp; pr < nch * n_rows; pr += kDwWarps) {
-        const int ch = pr / n_rows, orow = pr - ch * n_rows;
-        const int k = k0 + ch, oh = oh0 + orow;
+    const bool acc_out = ep.out_kind == QB200_OUT_ACC;
+    const int n_pr = flat ? nch : nch * n_rows;
+    for (int pr = warp; pr < n_pr; pr += kDwWarps) {
+        const int ch = flat ? pr : pr / n_rows;
+        const int orow_fixed = flat ? 0 : pr - ch * n_rows;
+        const int k = k0 + ch;
         const float scale = __fmul_rn(es.s_a, __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k)));
         const float bias = ep.bias ? __ldg(ep.bias + k) : 0.f;
         const int* wk = wsm + ch * taps;
-        const uint8_t* pbase = patch + ((size_t)ch * in_h + orow * g.stride) * in_w_alloc;
-        const int h_in = oh * g.stride - g.pad;
-        int w9[KS ? KS * KS : 1], wall = 0;
+        const int* wc = wcls + ch * 16;
+        const uint8_t* pch = patch + (size_t)ch * in_h * in_w_alloc;
+        // outputs of a channel band are contiguous: idx = base + orow * Q + ow  (= base + item index when flat)
+        const int64_t base = (((int64_t)n * g.K + k) * g.P + oh0 + orow_fixed) * g.Q;
+        int w9[KS ? KS * KS : 1];
+        uint32_t wpack[KS ? KS : 1];   // a filter row as the 4 bytes of a dp4a operand (KS <= 4)
         if (KS) {
 #pragma unroll
-            for (int i = 0; i < KS * KS; ++i) { w9[i] = wk[i]; wall += w9[i]; }
+            for (int i = 0; i < KS * KS; ++i) w9[i] = wk[i];
+#pragma unroll
+            for (int r = 0; r < KS; ++r) {
+                wpack[r] = 0;
+#pragma unroll
+                for (int s2 = 0; s2 < KS; ++s2) wpack[r] |= ((uint32_t)w9[r * KS + s2] & 0xFFu) << (8 * s2);
+            }
         }
-        const bool rows_in = KS && h_in >= 0 && h_in + KS <= g.H;
-        for (int ow = lane; ow < g.Q; ow += 32) {
-            const int w_in = ow * g.stride - g.pad;
-            const uint8_t* pp = pbase + ow * g.stride;
+        const int n_items = flat ? n_rows * g.Q : g.Q;
+        for (int it = lane; it < n_items; it += 32) {
+            int orow = orow_fixed, ow = it;
+            if (flat) {
+                orow = (int)(((uint32_t)it * magic_q) >> 16);
+                ow = it - orow * g.Q;
+            }
+            const int h_in = (oh0 + orow) * g.stride - g.pad, w_in = ow * g.stride - g.pad;
             int acc = 0, ws = 0;
             if (KS) {
+                // a row's KS taps = one dp4a on the 4 bytes starting at the output's column (two aligned words + a funnel
+                // shift; the byte past the filter meets a zero weight)
+                const int col0 = ow * g.stride;
+                const uint32_t* row32 = reinterpret_cast<const uint32_t*>(pch + (size_t)(orow * g.stride) * in_w_alloc) + (col0 >> 2);
+                const int sh = (col0 & 3) * 8;
 #pragma unroll
-                for (int r = 0; r < KS; ++r)
-#pragma unroll
-                    for (int s2 = 0; s2 < KS; ++s2) acc += (int)pp[r * in_w_alloc + s2] * w9[r * KS + s2];
-                if (rows_in && w_in >= 0 && w_in + KS <= g.W) {
-                    ws = wall;
+                for (int r = 0; r < KS; ++r) {
+                    const uint32_t* rr = row32 + r * (in_w_alloc >> 2);
+                    const uint32_t a = __funnelshift_r(rr[0], rr[1], sh);
+                    if (kSignedW) asm("dp4a.u32.s32 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(wpack[r]));
+                    else asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(a), "r"(wpack[r]));
+                }
+                if (cls_ok) {
+                    const int cls = (h_in < 0 ? 1 : 0) | (h_in + KS > g.H ? 2 : 0) | (w_in < 0 ? 4 : 0) | (w_in + KS > g.W ? 8 : 0);
+                    ws = wc[cls];
                 } else {
 #pragma unroll
                     for (int r = 0; r < KS; ++r)
@@ -102,6 +183,7 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
                             ws += (h_in + r >= 0 && h_in + r < g.H && w_in + s2 >= 0 && w_in + s2 < g.W) ? w9[r * KS + s2] : 0;
                 }
             } else {
+                const uint8_t* pp = pch + (size_t)(orow * g.stride) * in_w_alloc + ow * g.stride;
                 for (int r = 0; r < g.R; ++r) {
                     const bool rok = h_in + r >= 0 && h_in + r < g.H;
                     for (int s2 = 0; s2 < g.S; ++s2) {
@@ -111,8 +193,8 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
                     }
                 }
             }
-            const int64_t idx = (((int64_t)n * g.K + k) * g.P + oh) * g.Q + ow;
-            if (ep.out_kind == QB200_OUT_ACC) {
+            const int64_t idx = base + it;
+            if (acc_out) {
                 static_cast<int32_t*>(out)[idx] = acc;
             } else {
                 float t = (float)acc;
@@ -136,12 +218,12 @@ int launch_conv_dw_fused(const ConvGeom& g, const float* x, const uint8_t* wq, c
     const int TH = std::min(16, g.P);
     const int bands = (g.P + TH - 1) / TH;
     const int in_h = (TH - 1) * g.stride + g.R, in_w = (g.Q - 1) * g.stride + g.S;
-    const int in_w_alloc = (in_w + 3) & ~3;
+    const int in_w_alloc = (in_w + 7) & ~3;   // 4-byte rows with one spare word: the stencil reads aligned word pairs
     QB_REQUIRE((size_t)in_h * in_w_alloc <= 40 * 1024, QB200_EUNSUPPORTED, "conv_dw: plane too wide");
     int CH = std::max(1, 8192 / (TH * g.Q));
     CH = std::min(CH, std::min(64, g.K));
     while (CH > 1 && (size_t)CH * in_h * in_w_alloc > 40 * 1024) --CH;
-    const size_t smem = (((size_t)CH * in_h * in_w_alloc + 15) & ~(size_t)15) + (size_t)CH * g.R * g.S * sizeof(int);
+    const size_t smem = (((size_t)CH * in_h * in_w_alloc + 15) & ~(size_t)15) + (size_t)CH * (g.R * g.S + 16) * sizeof(int);
     const int kgroups = (g.K + CH - 1) / CH;
     const dim3 grid((unsigned)(kgroups * bands), (unsigned)g.N);
     const bool k3 = g.R == 3 && g.S == 3;
