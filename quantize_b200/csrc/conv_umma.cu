@@ -22,6 +22,8 @@
 #include "quant_math.cuh"
 
 #include <cuda.h>
+#include <cstdint>
+#include <climits>
 
 #include <type_traits>
 
@@ -1129,7 +1131,21 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     const int sms = num_sms();
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
-    while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
+    const int64_t k_gemm = (int64_t)gm.R * gm.S * gm.Cp;
+    if (k_gemm >= 1024 && !fq) {
+        // deep reductions are bound by the operand feed (L2 -> SM, ~40 GB/s per SM): per tile k_gemm * (128 + BN) bytes,
+        // and a partly filled last wave costs a whole tile time.  Pick the tile width with the least waves * bytes.
+        int best = BN;
+        int64_t best_cost = INT64_MAX;
+        for (int cand = BN; cand >= 64; cand >>= 1) {
+            const int64_t tiles = (int64_t)prm.m_tiles * ((g.K + cand - 1) / cand);
+            const int64_t cost = ((tiles + sms - 1) / sms) * (kBM + cand);
+            if (cost < best_cost) { best_cost = cost; best = cand; }
+        }
+        BN = best;
+    } else {
+        while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
+    }
     prm.BN = BN;
     // more tiles in flight where they are small: the MMA of tile i+3 need not wait for the epilogue of tile i+1
     prm.n_acc = BN <= 128 ? 4 : 2;
