@@ -410,7 +410,9 @@ def run_b200(args):
                                   chain_blocks=not args.no_chain, cross_block=not args.no_chain)
         hw = models.INPUT_HW[args.model]
         host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
-        host_out = torch.empty(args.batch, 1000, dtype=torch.float32).pin_memory()
+        with torch.no_grad():
+            n_classes = net(torch.zeros(1, 3, hw, hw, device=device)).shape[1]
+        host_out = torch.empty(args.batch, n_classes, dtype=torch.float32).pin_memory()
         dev_in = [torch.empty_like(host_in, device=device) for _ in range(2)]
         copy_stream = torch.cuda.Stream(device=device)
         compute = torch.cuda.current_stream()
