@@ -209,6 +209,18 @@ int qb200_quantconv2d_weightonly(const qb200_conv_shape* s, const float* x, cons
                                  const float* w_scale, const float* w_zero, int32_t n_w_scale,
                                  const float* bias, float* out, void* stream);
 
+/* quantlinear_float_input, weight-only semantic of the reference op
+ * (engine/kernels/functions/quantlinear_float_input.cu:36-106 kernel, :120-182 host):
+ *   out[b, o] = ( sum_k x[b, k] * ((qw[o, k] - w_zero[o|0]) * w_scale[o|0]) ) + bias[o]
+ * fp32, k ascending with fused multiply-adds and the bias added last — the reference kernel's order, so results are
+ * bit-identical to it whenever in_features is a multiple of 32 (its shared tiles keep stale entries otherwise).
+ * w_packed: the tpack stream of the [out_features, in_features] integer weights.
+ * The activation-quantized integer path of a linear layer is the 1x1 case of the convolution: call
+ * qb200_quantconv2d_fused with N = batch, C = Cg = in_features, H = W = 1, K = out_features, R = S = 1. */
+int qb200_quantlinear_weightonly(const float* x, int64_t batch, int32_t in_features, int32_t out_features,
+                                 const uint8_t* w_packed, int32_t w_bits, int32_t w_sign, const float* w_scale,
+                                 const float* w_zero, int32_t n_w_scale, const float* bias, float* out, void* stream);
+
 /* Max pooling over fp32 NCHW planes (planes = N*C), square kernel / stride, -inf padding, floor output size:
  * the op between the stem conv and the first residual stage of the ResNet family (torchvision resnet.py; the reference
  * runs torch.nn.MaxPool2d there).  Bit-identical to torch.nn.functional.max_pool2d; exists because that op, not a

@@ -129,3 +129,19 @@ def quantconv2d_float_input(x, w_packed, w_des, w_scale, w_zero, bias, stride, p
                                      n_bits, sign, None if b is None else _p(b), _p(out),
                                      N, C, H, W, K, R, S, stride, pad)
     return out
+
+
+def quantlinear_float_input(x, w_packed, w_des, w_scale, w_zero, bias):
+    """quantlinear_float_input.cu:36-106 weight-only semantic (sequential fp32 FMA accumulate, bias last)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    B, in_f = x.shape
+    n_bits, sign, out_f, in_w = [int(v) for v in np.asarray(w_des)[:4]]
+    assert in_w == in_f
+    w_scale = np.ascontiguousarray(np.asarray(w_scale, dtype=np.float32).reshape(-1))
+    w_zero = np.ascontiguousarray(np.asarray(w_zero, dtype=np.float32).reshape(-1))
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    w_packed = np.ascontiguousarray(w_packed, dtype=np.uint8)
+    out = np.empty((B, out_f), dtype=np.float32)
+    lib().qo_quantlinear_float_input(_p(x), _p(w_packed), _p(w_scale), _p(w_zero), int(w_scale.size == 1), n_bits, sign,
+                                     None if b is None else _p(b), _p(out), B, in_f, out_f)
+    return out

@@ -3,7 +3,8 @@
 Recipe (no reference build system is run; the sources are compiled where they lie):
   nvcc  /root/reference/engine/kernels/tpack/tpack.cu
   nvcc  /root/reference/engine/kernels/functions/quantconv2d_float_input.cu
-  g++   oracle/ref_bind.cpp   (our own 3-op pybind shim, includes the reference headers)
+  nvcc  /root/reference/engine/kernels/functions/quantlinear_float_input.cu
+  g++   oracle/ref_bind.cpp   (our own 4-op pybind shim, includes the reference headers)
   link  -> oracle/_ref/quant_engine_ref.so   (git-ignored; travels to the GPU box with gpurun)
 
 The reference tpack/tunpack have a CPU path (tpack.cu:140-190, :371-419) so they run in the CPU
@@ -55,21 +56,23 @@ def build(force=False):
         (nvcc + ["-c", os.path.join(KERN, "tpack", "tpack.cu"), "-o", os.path.join(OUT, "tpack.o")]),
         (nvcc + ["-c", os.path.join(KERN, "functions", "quantconv2d_float_input.cu"),
                  "-o", os.path.join(OUT, "quantconv2d_float_input.o")]),
+        (nvcc + ["-c", os.path.join(KERN, "functions", "quantlinear_float_input.cu"),
+                 "-o", os.path.join(OUT, "quantlinear_float_input.o")]),
         (gxx + ["-c", os.path.join(HERE, "ref_bind.cpp"), "-o", os.path.join(OUT, "ref_bind.o")]),
     ]
-    with ThreadPoolExecutor(3) as ex:
+    with ThreadPoolExecutor(4) as ex:
         for r in ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs):
             if r.returncode != 0:
                 raise RuntimeError("reference build failed:\n" + r.stderr[-4000:])
     link = ["g++", "-shared", "-o", so,
             os.path.join(OUT, "tpack.o"), os.path.join(OUT, "quantconv2d_float_input.o"),
-            os.path.join(OUT, "ref_bind.o"),
+            os.path.join(OUT, "quantlinear_float_input.o"), os.path.join(OUT, "ref_bind.o"),
             f"-L{libdir}", "-L/usr/local/cuda/lib64", "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python",
             "-lc10_cuda", "-ltorch_cuda", "-lcudart", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference link failed:\n" + r.stderr[-4000:])
-    for o in ("tpack.o", "quantconv2d_float_input.o", "ref_bind.o"):
+    for o in ("tpack.o", "quantconv2d_float_input.o", "quantlinear_float_input.o", "ref_bind.o"):
         os.remove(os.path.join(OUT, o))
     return so
 

@@ -172,3 +172,33 @@ void qo_quantconv2d_float_input(const float* x, const uint8_t* w_packed, const f
                     out[(((int64_t)n * K + k) * P + p) * Q + q] = o;                  /* :119 */
                 }
 }
+
+/* ---- engine/kernels/functions/quantlinear_float_input.cu:36-106: weight-only linear -----------------
+ * acc = 0; acc += x[b,k] * wf[o,k] for k ascending (:94-96; nvcc contracts to FFMA); out = acc + bias (:103-104).
+ * The reference kernel walks 32-wide shared tiles and, when input_size is not a multiple of 32, multiplies stale tile
+ * entries of the last pass (:66-68, :71 guard the loads, :94 does not guard the loop); this restatement sums exactly the
+ * input_size terms, so it equals the reference for input_size % 32 == 0. */
+void qo_quantlinear_float_input(const float* x, const uint8_t* w_packed, const float* w_scale, const float* w_zero,
+                                int per_tensor, int n_bits, int sign, const float* bias, float* out,
+                                int batch, int in_f, int out_f)
+{
+    const uint8_t offset = sign ? (uint8_t)(1 << (n_bits - 1)) : 0;   /* :163 */
+    const uint8_t mask = (uint8_t)((1 << n_bits) - 1);
+#pragma omp parallel for collapse(2)
+    for (int b = 0; b < batch; ++b)
+        for (int o = 0; o < out_f; ++o) {
+            float acc = 0.0f;                                                     /* :60 */
+            for (int k = 0; k < in_f; ++k) {
+                const int64_t e = (int64_t)o * in_f + k;                          /* :73 */
+                const int64_t byte = e * n_bits / 8;                              /* :74 */
+                const int bit = (int)(e * n_bits % 8);                            /* :75 */
+                uint8_t v = (uint8_t)((w_packed[byte] >> bit) & mask);            /* :76 */
+                if (bit + n_bits > 8) v |= (uint8_t)((w_packed[byte + 1] << (8 - bit)) & mask);   /* :77-78 */
+                v = (uint8_t)(v - offset);                                        /* :81 */
+                const float wv = sign ? (float)(int8_t)v : (float)v;              /* :82 */
+                const float wf = per_tensor ? (wv - w_zero[0]) * w_scale[0] : (wv - w_zero[o]) * w_scale[o];   /* :83-85 */
+                acc = fmaf(x[(int64_t)b * in_f + k], wf, acc);                    /* :95 */
+            }
+            out[(int64_t)b * out_f + o] = acc + (bias ? bias[o] : 0.0f);          /* :104 */
+        }
+}

@@ -107,6 +107,51 @@ weightonly_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_pac
     out[(((int64_t)n * g.K + k) * g.P + p) * g.Q + q] = o;              // :119
 }
 
+// ------------------------------------------------------------------------------------------------
+// weight-only fp32 linear (reference order: quantlinear_float_input.cu:60-105): acc = 0; acc = fma(x[k], wf[k], acc)
+// for k ascending (nvcc contracts the reference's `+= a * b`); out = acc + bias.  Block = 32 output features x 8 rows;
+// a 32 x 32 tile of dequantized weights is staged in shared memory per pass (each weight is unpacked once per 8 rows).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+linear_weightonly_kernel(const float* __restrict__ x, const uint8_t* __restrict__ w_packed, const float* __restrict__ w_scale,
+                         const float* __restrict__ w_zero, int per_tensor, int nb, int sign, const float* __restrict__ bias,
+                         float* __restrict__ out, int batch, int in_f, int out_f) {
+    __shared__ float wt[32][33];   // [k][col]
+    __shared__ float xt[8][32];    // [row][k]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + tx, row = blockIdx.y * 8 + ty;
+    const uint32_t offset = sign ? (1u << (nb - 1)) : 0u;
+    const uint32_t mask = (1u << nb) - 1u;
+    float acc = 0.f;
+    for (int k0 = 0; k0 < in_f; k0 += 32) {
+        // weights: thread (ty, tx) dequantizes rows ty, ty+8, ty+16, ty+24 of the k-tile for column blockIdx.x*32 + tx
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int kk = ty + 8 * j;
+            float wv = 0.f;
+            if (k0 + kk < in_f && col < out_f) {
+                const int64_t e = (int64_t)col * in_f + k0 + kk;            // :73
+                const int64_t bit = e * nb;
+                const int64_t byte = bit >> 3;                               // :74
+                const int off = (int)(bit & 7);                              // :75
+                uint32_t v = (w_packed[byte] >> off) & mask;                 // :76
+                if (off + nb > 8) v |= ((uint32_t)w_packed[byte + 1] << (8 - off)) & mask;   // :77-78
+                const uint8_t u = (uint8_t)(v - offset);                     // :81
+                const float f = sign ? (float)(int8_t)u : (float)u;          // :82
+                const float zero = per_tensor ? w_zero[0] : w_zero[col], scale = per_tensor ? w_scale[0] : w_scale[col];
+                wv = __fmul_rn(__fsub_rn(f, zero), scale);                   // :83-85
+            }
+            wt[kk][tx] = wv;
+        }
+        xt[ty][tx] = (row < batch && k0 + tx < in_f) ? __ldg(x + (int64_t)row * in_f + k0 + tx) : 0.f;   // :66-68
+        __syncthreads();
+        const int kn = min(32, in_f - k0);
+        for (int j = 0; j < kn; ++j) acc = __fmaf_rn(xt[ty][j], wt[j][tx], acc);   // :94-96
+        __syncthreads();
+    }
+    if (row < batch && col < out_f) out[(int64_t)row * out_f + col] = __fadd_rn(acc, bias ? bias[col] : 0.f);   // :103-104
+}
+
 }  // namespace
 
 int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
@@ -142,6 +187,23 @@ int qb200_quantconv2d_weightonly(const qb200_conv_shape* s, const float* x, cons
     QB_REQUIRE(g.K <= 65535 && g.N <= 65535, QB200_EUNSUPPORTED, "weightonly: K and N must be <= 65535");
     weightonly_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x, w_packed, w_scale, w_zero, n_w_scale == 1, s->w_bits, s->w_sign, bias, out, g);
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+
+int qb200_quantlinear_weightonly(const float* x, int64_t batch, int32_t in_features, int32_t out_features,
+                                 const uint8_t* w_packed, int32_t w_bits, int32_t w_sign, const float* w_scale,
+                                 const float* w_zero, int32_t n_w_scale, const float* bias, float* out, void* stream) {
+    using namespace qb200;
+    QB_REQUIRE(batch >= 0 && in_features > 0 && out_features > 0, QB200_EINVAL, "quantlinear: bad sizes");
+    QB_REQUIRE(w_bits > 0 && w_bits <= 8, QB200_EINVAL, "n_bits must be in the range (0, 8]");
+    QB_REQUIRE(n_w_scale == 1 || n_w_scale == out_features, QB200_EINVAL, "weight_scale must have 1 or out_features elements");
+    if (batch == 0) return 0;
+    QB_REQUIRE(x && w_packed && w_scale && w_zero && out, QB200_EINVAL, "quantlinear: null pointer");
+    QB_REQUIRE((batch + 7) / 8 <= 65535, QB200_EUNSUPPORTED, "quantlinear: batch too large");
+    const dim3 grid((unsigned)((out_features + 31) / 32), (unsigned)((batch + 7) / 8));
+    linear_weightonly_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w_packed, w_scale, w_zero, n_w_scale == 1, w_bits, w_sign, bias, out, (int)batch, in_features, out_features);
     QB_LAUNCH_CHECK();
     return 0;
 }

@@ -224,6 +224,12 @@ const float* device_float(const py::object& o, const at::Device& dev, std::vecto
 // ------------------------------------------------------------------------------------------------
 // quantconv2d_float_input
 // ------------------------------------------------------------------------------------------------
+at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des, const std::vector<int64_t>& d,
+                     const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias,
+                     const int stride, const int padding, const py::object& input_scale, const py::object& input_zero,
+                     const py::object& input_qmin, const py::object& input_qmax, const c10::optional<at::Tensor>& residual,
+                     const bool fuse_relu);
+
 at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des,
                                    const at::Tensor& weight_scale, const at::Tensor& weight_zero,
                                    const c10::optional<at::Tensor>& bias, const int stride, const int padding,
@@ -249,6 +255,16 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
 
     const std::vector<int64_t>& d = host_des(weight_des);
     TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+    return conv_core(input, weight, weight_des, d, weight_scale, weight_zero, bias, stride, padding, input_scale, input_zero,
+                     input_qmin, input_qmax, residual, fuse_relu);
+}
+
+// (g_mu held, device guard set) d = [n_bits, sign, K, Cg, R, S]; input is 4-D
+at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des, const std::vector<int64_t>& d,
+                     const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias,
+                     const int stride, const int padding, const py::object& input_scale, const py::object& input_zero,
+                     const py::object& input_qmin, const py::object& input_qmax, const c10::optional<at::Tensor>& residual,
+                     const bool fuse_relu) {
     qb200_conv_shape s;
     s.N = (int32_t)input.size(0);
     s.C = (int32_t)input.size(1);
@@ -529,9 +545,51 @@ at::Tensor quantlinear(const at::Tensor&, const at::Tensor&, const at::Tensor&, 
                        const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&) {
     off_path("quantlinear");
 }
-at::Tensor quantlinear_float_input(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
-                                   const at::Tensor&, const c10::optional<at::Tensor>&) {
-    off_path("quantlinear_float_input");
+// quantlinear_float_input (reference quantlinear_float_input.cu:120-182, funcs.h).  The six positional
+// arguments are the reference's: weight-only fp32 semantic in the reference kernel's accumulation order.  With the
+// activation quantizer's parameters (input_scale / zero / qmin / qmax, as for the conv op) the layer runs as the 1x1 case
+// of the fused integer convolution: M = batch (x tokens) rows through the tensor-core kernel.
+at::Tensor quantlinear_float_input(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des,
+                                   const at::Tensor& weight_scale, const at::Tensor& weight_zero,
+                                   const c10::optional<at::Tensor>& bias, const py::object& input_scale,
+                                   const py::object& input_zero, const py::object& input_qmin, const py::object& input_qmax) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    CHECK_INPUT(weight);
+    CHECK_INPUT(weight_des);
+    CHECK_INPUT(weight_scale);
+    CHECK_INPUT(weight_zero);
+    if (bias.has_value()) { CHECK_INPUT(bias.value()); }
+    TORCH_CHECK(input.dim() == 2, "input must be a 2D tensor (batch_size, input_size)");
+    TORCH_CHECK(weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
+    CHECK_FLOAT(weight_scale);
+    CHECK_FLOAT(weight_zero);
+    if (bias.has_value()) { TORCH_CHECK(bias.value().dtype() == torch::kFloat32, "bias must be a float tensor"); }
+    c10::cuda::CUDAGuard guard(input.device());
+    std::lock_guard<std::mutex> lock(g_mu);
+    const std::vector<int64_t>& d = host_des(weight_des);
+    TORCH_CHECK(d.size() >= 4, "weight_des must hold [n_bits, sign, out_features, in_features]");
+    const int64_t B = input.size(0), in_f = input.size(1), out_f = d[2];
+    TORCH_CHECK(d[3] == in_f, "input has ", in_f, " features, the weight expects ", d[3]);
+    TORCH_CHECK(weight.numel() >= qb200_packed_bytes(out_f * in_f, (int)d[0]), "weight is shorter than weight_des describes");
+    const int64_t n_ws = weight_scale.numel();
+    TORCH_CHECK(n_ws == 1 || n_ws == out_f, "weight_scale must have 1 or ", out_f, " elements");
+    TORCH_CHECK(weight_zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
+    if (bias.has_value()) TORCH_CHECK(bias.value().numel() == out_f, "bias must have ", out_f, " elements");
+    if (input_scale.is_none()) {
+        auto out = at::empty({B, out_f}, input.options());
+        check_rc(qb200_quantlinear_weightonly(input.data_ptr<float>(), B, (int32_t)in_f, (int32_t)out_f, weight.data_ptr<uint8_t>(),
+                                              (int32_t)d[0], d[1] != 0, weight_scale.data_ptr<float>(),
+                                              weight_zero.data_ptr<float>(), (int32_t)n_ws,
+                                              bias.has_value() ? bias.value().data_ptr<float>() : nullptr,
+                                              out.data_ptr<float>(), cur_stream()),
+                 "quantlinear_float_input");
+        return out;
+    }
+    const std::vector<int64_t> d6 = {d[0], d[1], out_f, in_f, 1, 1};
+    auto out4 = conv_core(input.view({B, in_f, 1, 1}), weight, weight_des, d6, weight_scale, weight_zero, bias, 1, 0, input_scale,
+                          input_zero, input_qmin, input_qmax, c10::nullopt, false);
+    return out4.view({B, out_f});
 }
 at::Tensor conv2d(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int, int, int) { off_path("conv2d"); }
 at::Tensor quantconv2d(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
@@ -548,7 +606,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("linear", &linear, "Linear function.", py::arg("input"), py::arg("weight"), py::arg("bias") = py::none(),
           py::arg("mode") = 0);
     m.def("quantlinear", &quantlinear, "Quantized linear function.");
-    m.def("quantlinear_float_input", &quantlinear_float_input, "Quantized linear function with float input.");
+    m.def("quantlinear_float_input", &quantlinear_float_input, "Quantized linear function with float input.",
+          py::arg("input"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
+          py::arg("bias") = py::none(), py::arg("input_scale") = py::none(), py::arg("input_zero") = py::none(),
+          py::arg("input_qmin") = py::none(), py::arg("input_qmax") = py::none());
     m.def("conv2d", &conv2d, "Conv2d function.", py::arg("input"), py::arg("weight"), py::arg("bias"), py::arg("stride"),
           py::arg("padding"), py::arg("mode") = 0);
     m.def("quantconv2d", &quantconv2d, "Quantized conv2d function.");

@@ -71,3 +71,20 @@ def test_weightonly_matches_float_conv():
                 patch = xp[:, :, p * stride:p * stride + R, q * stride:q * stride + S]
                 ref[:, :, p, q] = np.einsum("ncrs,kcrs->nk", patch, wf) + bias
         assert np.allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_linear_oracle_against_float64():
+    """quantlinear_float_input restatement (weight-only): sequential fp32 FMA sum vs an exact float64 product."""
+    rng = np.random.default_rng(3)
+    B, in_f, out_f = 5, 70, 9
+    x = rng.standard_normal((B, in_f)).astype(np.float32)
+    qw = rng.integers(-8, 8, size=(out_f, in_f)).astype(np.int64)
+    packed, des = oracle.tpack(qw, 4, True)
+    w_scale = (rng.random(out_f) * 0.02 + 0.001).astype(np.float32)
+    w_zero = rng.integers(-2, 3, size=out_f).astype(np.float32)
+    bias = rng.standard_normal(out_f).astype(np.float32)
+    got = oracle.quantlinear_float_input(x, packed, des, w_scale, w_zero, bias)
+    wf = ((qw.astype(np.float32) - w_zero[:, None]) * w_scale[:, None]).astype(np.float64)
+    want = x.astype(np.float64) @ wf.T + bias
+    assert got.dtype == np.float32 and got.shape == (B, out_f)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-5)
