@@ -221,6 +221,12 @@ int qb200_quantlinear_weightonly(const float* x, int64_t batch, int32_t in_featu
                                  const uint8_t* w_packed, int32_t w_bits, int32_t w_sign, const float* w_scale,
                                  const float* w_zero, int32_t n_w_scale, const float* bias, float* out, void* stream);
 
+/* Quantizer.simulate of a per-tensor quantizer (modelzoo/modules/quantizer.py:194, :215-218) in one
+ * pass:  out = (clamp(rint(x / scale - zero), qmin, qmax) + zero) * scale,  each step rounded like the separate fp32
+ * torch kernels the reference launches (div, sub, round, clamp, add, mul) — bit-identical to them.  Any range
+ * (signed ranges and ranges beyond a byte take an IEEE-division path).  x, out: n fp32 values (may alias). */
+int qb200_fake_quantize_f32(const float* x, int64_t n, const qb200_act_quant* aq, float* out, void* stream);
+
 /* Max pooling over fp32 NCHW planes (planes = N*C), square kernel / stride, -inf padding, floor output size:
  * the op between the stem conv and the first residual stage of the ResNet family (torchvision resnet.py; the reference
  * runs torch.nn.MaxPool2d there).  Bit-identical to torch.nn.functional.max_pool2d; exists because that op, not a

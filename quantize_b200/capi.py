@@ -17,7 +17,7 @@ SYMBOLS = [
     "qb200_conv_workspace_bytes", "qb200_act_quantize_nhwc", "qb200_set_conv_algo", "qb200_get_conv_algo",
     "qb200_quantconv2d_fused", "qb200_conv2d_q8_nhwc", "qb200_quantconv2d_weightonly",
     "qb200_conv_quantize_input", "qb200_conv_from_workspace", "qb200_conv_is_single_kernel", "qb200_watchdog_code",
-    "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_quantlinear_weightonly",
+    "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_quantlinear_weightonly", "qb200_fake_quantize_f32",
 ]
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
@@ -86,6 +86,7 @@ def lib():
         L.qb200_conv_from_workspace_ex.argtypes = [sp, vp, vp, vp, i32, vp, ap, ctypes.POINTER(ConvTail), vp, i32, vp]
         L.qb200_conv_handoff_supported.argtypes = [sp, sp]
         L.qb200_maxpool2d_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp]
+        L.qb200_fake_quantize_f32.argtypes = [vp, i64, ap, vp, vp]
         L.qb200_quantlinear_weightonly.argtypes = [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp]
         _lib = L
     return _lib

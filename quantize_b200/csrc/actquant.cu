@@ -486,4 +486,56 @@ int launch_zero_pad_borders(uint8_t* q, int N, int H, int W, int pad, int Cp, cu
     return 0;
 }
 
+
+namespace {
+// Quantizer.simulate for a per-tensor quantizer as ONE elementwise pass (the reference runs five torch kernels:
+// div, sub, round, clamp, add*mul — quantizer.py:194, :215-218):  out = (clamp(rint(x / s - z), qmin, qmax) + z) * s,
+// every step rounded like the separate fp32 ops.
+__device__ __forceinline__ float fake_quant1(float x, const QuantParams& p) {
+    if (x != x) return x;   // torch's clamp propagates NaN
+    float q;
+    if (p.byte_clamp) {
+        q = (float)min(max(quant_int(x, p), p.ilo), p.ihi);
+    } else {
+        q = rintf(__fsub_rn(__fdiv_rn(x, p.s), p.z));
+        q = fminf(fmaxf(q, p.lo), p.hi);
+    }
+    return __fmul_rn(__fadd_rn(q, p.z), p.s);
+}
+
+__global__ void __launch_bounds__(256)
+fake_quantize_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, const float* __restrict__ p_scale,
+                     const float* __restrict__ p_zero, const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int64_t n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec) {
+        for (int64_t i = t0; i < n4; i += stride) {
+            const float4 v = ldg_stream4(x + 4 * i);
+            float4 o;
+            o.x = fake_quant1(v.x, p); o.y = fake_quant1(v.y, p); o.z = fake_quant1(v.z, p); o.w = fake_quant1(v.w, p);
+            reinterpret_cast<float4*>(out)[i] = o;
+        }
+        for (int64_t i = 4 * n4 + t0; i < n; i += stride) out[i] = fake_quant1(__ldg(x + i), p);
+    } else {
+        for (int64_t i = t0; i < n; i += stride) out[i] = fake_quant1(__ldg(x + i), p);
+    }
+}
+}  // namespace
+
 }  // namespace qb200
+
+extern "C" int qb200_fake_quantize_f32(const float* x, int64_t n, const qb200_act_quant* aq, float* out, void* stream) {
+    using namespace qb200;
+    QB_REQUIRE(n >= 0, QB200_EINVAL, "fake_quantize: negative size");
+    if (n == 0) return 0;
+    QB_REQUIRE(x && out && aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL, "fake_quantize: null pointer");
+    const int blocks = (int)std::min<int64_t>(ceil_div64(ceil_div64(n, 4), 256), (int64_t)kNumSMs * 16);
+    QB_CUDA(launch_pdl(fake_quantize_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), x, out, n, aq->scale,
+                       aq->zero, aq->qmin, aq->qmax));
+    QB_LAUNCH_CHECK();
+    return 0;
+}

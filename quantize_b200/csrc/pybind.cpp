@@ -514,6 +514,25 @@ py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, co
     return py::make_tuple(out, ws_emit.defined() ? py::cast(ws_emit) : py::none());
 }
 
+// fake_quantize: Quantizer.simulate of a per-tensor quantizer as one kernel
+at::Tensor fake_quantize(const at::Tensor& input, const py::object& scale, const py::object& zero, const py::object& qmin,
+                         const py::object& qmax) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    c10::cuda::CUDAGuard guard(input.device());
+    std::lock_guard<std::mutex> lock(g_mu);
+    std::vector<at::Tensor> keep;
+    qb200_act_quant aq;
+    aq.scale = device_float(scale, input.device(), keep, "scale");
+    aq.zero = device_float(zero, input.device(), keep, "zero");
+    aq.qmin = device_float(qmin, input.device(), keep, "qmin");
+    aq.qmax = device_float(qmax, input.device(), keep, "qmax");
+    auto out = at::empty_like(input);
+    check_rc(qb200_fake_quantize_f32(input.data_ptr<float>(), input.numel(), &aq, out.data_ptr<float>(), cur_stream()),
+             "fake_quantize");
+    return out;
+}
+
 // max_pool2d (engine helper for the packed ResNet forward; same result as torch.nn.functional.max_pool2d)
 at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int padding) {
     CHECK_INPUT(input);
@@ -622,6 +641,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           "Consecutive fused quantized convs with int8 activations handed from one layer's epilogue to the next.",
           py::arg("input"), py::arg("layers"), py::arg("residual") = py::none(), py::arg("input_handoff") = py::none(),
           py::arg("emit_next") = py::none());
+    m.def("fake_quantize", &fake_quantize,
+          "(clamp(round(x / scale - zero), qmin, qmax) + zero) * scale for a per-tensor quantizer, one kernel.",
+          py::arg("input"), py::arg("scale"), py::arg("zero"), py::arg("qmin"), py::arg("qmax"));
     m.def("max_pool2d", &max_pool2d, "fp32 NCHW max pooling (square kernel / stride, -inf padding, floor mode).",
           py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0);
     // engine-level helpers (not part of the reference surface)

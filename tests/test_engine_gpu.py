@@ -184,3 +184,27 @@ def test_quantlinear_argument_errors(engine):
         engine.quantlinear_float_input(torch.zeros(2, 31).cuda(), t(c["packed"]), t(c["des"]), t(c["w_scale"]), t(c["w_zero"]), None)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         engine.quantlinear_float_input(torch.zeros(2, 32), t(c["packed"]), t(c["des"]), t(c["w_scale"]), t(c["w_zero"]), None)
+
+
+@pytest.mark.parametrize("rng_", [(0, 255), (0, 15), (-128, 127), (-7, 7), (0, 65535)], ids=lambda r: "q{}_{}".format(*r))
+@pytest.mark.parametrize("n", [1, 1000003, 4096])
+def test_fake_quantize_matches_the_torch_ops(engine, rng_, n):
+    """Quantizer.simulate (quantizer.py:194, :215-218) as one kernel, bit-identical to the five
+    torch kernels of the reference — every range, rounding ties, values far outside the range, inf / NaN."""
+    qmin, qmax = rng_
+    g = torch.Generator().manual_seed(n + qmax)
+    x = (torch.randn(n, generator=g) * 3).cuda()
+    scale = torch.tensor([0.0371], device="cuda")
+    zero = torch.tensor([-40.3 if qmin == 0 else 0.0], device="cuda")
+    if n > 16:
+        ks = torch.arange(qmin - 3, qmin + 9, device="cuda", dtype=torch.float32)
+        x[:12] = (ks + 0.5 + zero) * scale                      # rounding ties (to even)
+        x[12:16] = torch.tensor([1e30, -1e30, float("inf"), float("nan")], device="cuda")
+    got = engine.fake_quantize(x, scale, zero, qmin, qmax)
+    want = (torch.clamp(torch.round(x / scale - zero), qmin, qmax) + zero) * scale
+    assert torch.equal(torch.isnan(got), torch.isnan(want))
+    assert torch.equal(got.nan_to_num(0.0), want.nan_to_num(0.0))
+    # a 4-D, non-16-byte-aligned view takes the scalar path
+    y = x[1:].contiguous()[: (n - 1) // 2 * 2].view(-1, 2) if n > 4 else x.view(1, 1)
+    assert torch.equal(engine.fake_quantize(y, scale, zero, qmin, qmax).nan_to_num(0.0),
+                       ((torch.clamp(torch.round(y / scale - zero), qmin, qmax) + zero) * scale).nan_to_num(0.0))

@@ -239,3 +239,23 @@ def test_state_dict_round_trip_keeps_reference_format():
     fresh.load_state_dict(sd)
     with torch.no_grad():
         assert torch.equal(fresh(x), want)
+
+
+def test_fake_quant_forward_through_the_engine_kernel_is_bit_identical():
+    """the unpacked (fake-quant) GPU forward with Quantizer.simulate on the engine's one-pass kernel
+    == the same forward on the five torch kernels per quantizer."""
+    model = models.build_quantized("resnet18", 8, 8, seed=0).cuda()
+    host.calibrate(model, models.synthetic_batch("resnet18", 4, 1, "cuda"))
+    x = models.synthetic_batch("resnet18", 3, device="cuda")
+    with torch.no_grad():
+        host.Quantizer.use_engine = False
+        try:
+            want = model(x)
+        finally:
+            host.Quantizer.use_engine = True
+        import quantize_b200.engine as E
+        qe = E.load()
+        qe._launch_count_reset()
+        got = model(x)
+        assert qe._launch_count() >= 20          # one engine kernel per activation quantizer
+    assert torch.equal(got, want)
