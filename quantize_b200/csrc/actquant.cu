@@ -348,6 +348,31 @@ act_quantize_im2col8_kernel(const float* __restrict__ x, uint8_t* __restrict__ a
     }
 }
 
+// H*W == 1 (linear layers as 1x1 convolutions): NCHW is already NHWC; one thread = one word of four channels
+__global__ void __launch_bounds__(256)
+act_quantize_rows_kernel(const float* __restrict__ x, uint32_t* __restrict__ q, int64_t words, int C, int Cp,
+                         const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                         const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int wpr = Cp >> 2;   // words per row
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / wpr;
+        const int c = (int)(i - n * wpr) * 4;
+        const float* xp = x + n * C + c;
+        float a[4];
+        uint32_t keep = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const bool in = c + b < C;
+            a[b] = in ? __ldg(xp + b) : 0.f;
+            if (in) keep |= 0xFFu << (8 * b);
+        }
+        q[i] = quant_word(a[0], a[1], a[2], a[3], p) & keep;
+    }
+}
+
 }  // namespace
 
 int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, const qb200_act_quant* aq, uint8_t* a_col,
@@ -398,7 +423,12 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((Cp + kCw - 1) / kCw));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const PadSpec ps{0, H, W};
-    if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
+    if (HW == 1) {
+        const int64_t words = (int64_t)N * (Cp >> 2);
+        const int blocks = (int)std::min<int64_t>(ceil_div64(words, 256), (int64_t)kNumSMs * 8);
+        QB_CUDA(launch_pdl(act_quantize_rows_kernel, dim3(blocks), dim3(256), 0, st, x, reinterpret_cast<uint32_t*>(q_nhwc), words, C, Cp,
+                           aq->scale, aq->zero, aq->qmin, aq->qmax));
+    } else if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
         QB_CUDA(launch_pdl(act_quantize_nhwc_vec4_kernel, dim3(grid), dim3(kThreads), 0, st, x, q_nhwc, total, C, Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
                                                                   aq->qmax));
     else

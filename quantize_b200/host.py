@@ -244,6 +244,60 @@ class QuantConv2d(nn.Conv2d):
         return torch.relu(out) if self.fuse_relu else out
 
 
+class QuantLinear(nn.Linear):
+    """reference modelzoo/modules/quantlinear.py:17-186 (no bias correction), packed forward routed through the engine's
+    quantlinear_float_input with the activation quantizer's parameters (the integer path: the 1x1 case of the conv)."""
+
+    def __init__(self, lin: nn.Linear, w_setting=None, a_setting=None):
+        super().__init__(lin.in_features, lin.out_features, lin.bias is not None)
+        self.weight.data = lin.weight.detach().clone()                                # quantlinear.py:77-79
+        if lin.bias is not None:
+            self.bias.data = lin.bias.detach().clone()
+        self.w_quantizer = Quantizer(**(w_setting or DEFAULT_W), flag="weight", n_channels=lin.out_features, dim=2)
+        self.a_quantizer = Quantizer(**(a_setting or DEFAULT_A), flag="activation", n_channels=lin.in_features, dim=2)
+        self.calibrating = False
+        self.packed = False
+        self.use_engine = True
+
+    def calibrate(self, x: Tensor):                                 # quantlinear.py:93-104
+        self.a_quantizer.calibrate(x.detach().clone())
+        self.w_quantizer.calibrate(self.weight.detach().clone())
+
+    def _forward(self, x: Tensor) -> Tensor:                        # quantlinear.py:106-121
+        if self.calibrating:
+            self.calibrate(x)
+        x = self.a_quantizer(x)
+        weight = self.w_quantizer(self.weight)
+        return nn.functional.linear(x, weight, self.bias)
+
+    @torch.no_grad()
+    def pack(self):                                                 # quantlinear.py:123-150
+        self.requires_grad_(False)
+        self.a_quantizer.pack(None)
+        weight, w_scale, w_zero = self.w_quantizer.pack(self.weight)
+        self.register_buffer("w_scale", w_scale)
+        self.register_buffer("w_zero", w_zero)
+        self.weight.data, w_des = _engine.load().tpack(weight.contiguous(), self.w_quantizer.n_bits, self.w_quantizer.signed)
+        self.register_buffer("w_des", w_des)
+        self.w_quantizer = None
+        self.packed = True
+
+    def forward(self, x: Tensor) -> Tensor:                         # quantlinear.py:152-163
+        if not self.packed:
+            return self._forward(x)
+        if self.use_engine and x.is_cuda:
+            a = self.a_quantizer
+            x2 = x.reshape(-1, self.in_features).contiguous()
+            out = _engine.load().quantlinear_float_input(x2, self.weight, self.w_des, self.w_scale.reshape(-1),
+                                                         self.w_zero.reshape(-1), self.bias, input_scale=a.scale,
+                                                         input_zero=a.zero, input_qmin=a.qmin, input_qmax=a.qmax)
+            return out.reshape(*x.shape[:-1], self.out_features)
+        # the reference's packed forward: float linear on dequantized operands
+        q, a_scale, a_zero = self.a_quantizer.simulate(x)
+        w = _engine.load().tunpack(self.weight, self.w_des)
+        return nn.functional.linear((q + a_zero).mul_(a_scale), (w + self.w_zero).mul_(self.w_scale), self.bias)
+
+
 class EngineMaxPool2d(nn.Module):
     """nn.MaxPool2d (square kernel / stride, no dilation, floor mode) on the engine's kernel; same values as torch."""
 
@@ -361,7 +415,7 @@ def fuse_resnet_blocks(model, chain=False, cross_block=False):
 def reconstruct(model: nn.Module, w_setting=None, a_setting=None) -> nn.Module:
     """reference modelzoo/reconstruct.py:15-41, :94-132 for Conv2d(+BatchNorm2d): a conv directly followed (in
     child order) by a BatchNorm2d is folded and the BN becomes Identity; other children are visited recursively.
-    nn.Linear layers are left in floating point (QuantLinear is off the hot path)."""
+    nn.Linear -> QuantLinear (reconstruct.py:115-117)."""
     names = [n for n, _ in model.named_children()]
     mods = dict(model.named_children())
     skip = set()
@@ -377,6 +431,8 @@ def reconstruct(model: nn.Module, w_setting=None, a_setting=None) -> nn.Module:
                 skip.add(names[i + 1])
             else:
                 setattr(model, name, QuantConv2d(m, None, w_setting, a_setting))
+        elif isinstance(m, nn.Linear) and not isinstance(m, QuantLinear):
+            setattr(model, name, QuantLinear(m, w_setting, a_setting))
         else:
             reconstruct(m, w_setting, a_setting)
     return model
@@ -406,6 +462,7 @@ def calibrate(model, batch):
 
 def pack(model):
     """the packing loop the reference keeps commented out (runner/ptq.py:106-114)."""
-    for m in quant_layers(model):
-        m.pack()
+    for m in model.modules():
+        if isinstance(m, (QuantConv2d, QuantLinear)):
+            m.pack()
     return model

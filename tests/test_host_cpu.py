@@ -70,10 +70,10 @@ def test_resnet20_reconstruct_matches_reference_reconstruct():
     float_model.eval()
     import copy
     ref_model = ref_reconstruct(copy.deepcopy(float_model), cfg.quant)
-    # the reference also quantizes nn.Linear (QuantLinear, off the hot path): put the float FC back for the comparison
-    ref_model.fc = copy.deepcopy(float_model.fc)
+    # (the reference also rebuilds nn.Linear as QuantLinear, reconstruct.py:115-117; so does the mirror)
     mine = host.reconstruct(copy.deepcopy(float_model))
-    assert len(host.quant_layers(mine)) == 21
+    assert len(host.quant_layers(mine)) == 21 and isinstance(mine.fc, host.QuantLinear)
+    assert ref_model.fc.__class__.__name__ == "QuantLinear"
     x = torch.randn(4, 3, 32, 32)
     with torch.no_grad():
         host.calibrate(mine, x)

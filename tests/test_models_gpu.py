@@ -31,7 +31,7 @@ def _compare(name, batch, w_bits, a_bits):
     with torch.no_grad():
         ref = model(x).clone()                       # fake-quant forward (quantconv2d.py:154-168)
     packed = host.pack(copy.deepcopy(model))
-    layers = host.quant_layers(packed)
+    layers = [m for m in packed.modules() if isinstance(m, (host.QuantConv2d, host.QuantLinear))]
     worst = [0.0]
 
     def check_layer(m, inp, out):
@@ -54,7 +54,10 @@ def _compare(name, batch, w_bits, a_bits):
             m.use_engine = False
         out_ref_packed = packed(x)
     scale = ref.abs().max()
-    e2e_tol = 1e-2 if a_bits >= 8 else 5e-2      # one 4-bit quantization step is 1/15 of a layer's range
+    # network level (the rigorous check is the per-layer one above): a value on a rounding boundary may flip by one
+    # level in one path and not the other; one 4-bit level is 1/15 of a layer's range and, now that the classifier is
+    # quantized too (QuantLinear), a flip in its input reaches the logits directly
+    e2e_tol = 1e-2 if a_bits >= 8 else 1e-1
     assert (out - ref).abs().max() <= e2e_tol * scale, float((out - ref).abs().max() / scale)
     assert (out - out_ref_packed).abs().max() <= e2e_tol * scale
     assert torch.equal(out.argmax(1), ref.argmax(1))           # top-1 agreement 100 %
