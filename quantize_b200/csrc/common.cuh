@@ -27,6 +27,7 @@ void count_launch(int n = 1);
         if (_e != cudaSuccess) {                                                          \
             ::qb200::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
                                __FILE__, __LINE__);                                       \
+            (void)cudaGetLastError(); /* do not leave a non-sticky error for the next launch check */ \
             return (int)_e;                                                               \
         }                                                                                 \
     } while (0)

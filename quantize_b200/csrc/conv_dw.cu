@@ -222,8 +222,12 @@ int launch_conv_dw_fused(const ConvGeom& g, const float* x, const uint8_t* wq, c
     QB_REQUIRE((size_t)in_h * in_w_alloc <= 40 * 1024, QB200_EUNSUPPORTED, "conv_dw: plane too wide");
     int CH = std::max(1, 8192 / (TH * g.Q));
     CH = std::min(CH, std::min(64, g.K));
-    while (CH > 1 && (size_t)CH * in_h * in_w_alloc > 40 * 1024) --CH;
-    const size_t smem = (((size_t)CH * in_h * in_w_alloc + 15) & ~(size_t)15) + (size_t)CH * (g.R * g.S + 16) * sizeof(int);
+    auto smem_of = [&](int ch) {
+        return (((size_t)ch * in_h * in_w_alloc + 15) & ~(size_t)15) + (size_t)ch * (g.R * g.S + 16) * sizeof(int);
+    };
+    while (CH > 1 && smem_of(CH) > 48 * 1024) --CH;   // patch + filter tables within the default dynamic shared memory
+    const size_t smem = smem_of(CH);
+    QB_REQUIRE(smem <= 48 * 1024, QB200_EUNSUPPORTED, "conv_dw: plane too wide");
     const int kgroups = (g.K + CH - 1) / CH;
     const dim3 grid((unsigned)(kgroups * bands), (unsigned)g.N);
     const bool k3 = g.R == 3 && g.S == 3;
