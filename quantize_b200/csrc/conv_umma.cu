@@ -772,10 +772,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 pq = row_ok ? (int)(m - (int64_t)img * PQ) : 0;
             }
             const int p = prm.fd_q.div(pq), q = pq - p * g.Q;
-            const PixelWindow pw = pixel_window(g, p, q);
+            // int8-only hand-off instantiation (two epilogue groups): its per-tile bookkeeping is a third of the warp's
+            // instructions on 64-channel tiles, so the tap-window work is skipped when the zero point is 0 (inputs that
+            // follow a ReLU), where every pixel is "interior" by definition
+            constexpr bool kLightSetup = kQ8 && kGroups == 2;
+            const bool need_win = !kLightSetup || es.z_a != 0.f;
+            PixelWindow pw = {0, g.R, 0, g.S};
+            if (need_win) pw = pixel_window(g, p, q);
             const bool interior = es.z_a == 0.f || (pw.r0 == 0 && pw.r1 == g.R && pw.s0 == 0 && pw.s1 == g.S);
             // without a class table, a warp with any border pixel computes the window form for all its lanes
-            const bool warp_interior = __all_sync(0xffffffffu, interior || !row_ok);
+            const bool warp_interior = need_win ? __all_sync(0xffffffffu, interior || !row_ok) : true;
             const bool full_n = k_base + BN <= g.K;
             // this pixel's row of window sums: its class in the shared table, else the full-window sums
             const float* wrow = be;
@@ -862,7 +868,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                 r[j] = tail(__fmaf_rn(sc[cc + j], __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]), br[cc + j]), j);
                             }
                         }
-                        if (ep.store_f32) {
+                        if (kGroups == 1 && ep.store_f32) {   // (the two-group instantiation is launched for int8-only output)
                             float* o = static_cast<float*>(out) + o_off;
                             if (full_n) {
 #pragma unroll
