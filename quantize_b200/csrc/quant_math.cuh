@@ -9,7 +9,7 @@ namespace qb200 {
 struct QuantParams {
     float s, z, lo, hi;  // the reference's parameters
     float r;             // RN(1/s)
-    float xlo, xhi;      // inputs outside [xlo, xhi] quantize to qmin / qmax whatever their value (2 steps of margin)
+    float xlo, xhi;      // inputs outside [xlo, xhi] quantize to qmin / qmax; xlo / xhi themselves quantize to exactly qmin / qmax
     int ilo, ihi;        // qmin / qmax as integers (valid when byte_clamp)
     int full_range;      // [qmin, qmax] == [0, 255]: the saturating pack is the whole clamp
     int byte_clamp;      // 0 <= qmin <= qmax <= 255, both integral, scale normal: the branch-free path applies
@@ -23,8 +23,12 @@ __device__ __forceinline__ QuantParams load_params(const float* p_scale, const f
     p.lo = __ldg(p_qmin);
     p.hi = __ldg(p_qmax);
     p.r = __frcp_rn(p.s);
-    p.xlo = __fmul_rn(__fadd_rn(__fadd_rn(p.lo, p.z), -2.f), p.s);
-    p.xhi = __fmul_rn(__fadd_rn(__fadd_rn(p.hi, p.z), 2.f), p.s);
+    // Tight input clamp: xlo = RN((qmin + z) * s) quantizes to exactly qmin (its t = RN(RN(xlo / s) - z) is within an ulp
+    // of qmin, far from the .5 boundary) and the computed quantizer is monotone in x (a chain of monotone roundings), so
+    // every clamped input lands in [qmin, qmax] and every input below / above the clamp would have been clamped to
+    // qmin / qmax by the reference anyway.  No saturation or integer clamp is needed after the rounding.
+    p.xlo = __fmul_rn(__fadd_rn(p.lo, p.z), p.s);
+    p.xhi = __fmul_rn(__fadd_rn(p.hi, p.z), p.s);
     const bool range_ok = p.lo >= 0.f && p.hi <= 255.f && p.lo <= p.hi && p.lo == rintf(p.lo) && p.hi == rintf(p.hi);
     // the division refinement below needs a normal positive scale with headroom and a bounded zero point
     const bool scale_ok = p.s > 1e-30f && p.s < 1e30f && fabsf(p.z) < 1048576.f;
@@ -91,26 +95,17 @@ __device__ __forceinline__ void quant_int2(float x0, float x1, const QuantParams
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(q) : "l"(q), "l"(magic));
     uint32_t u0, u1;
     asm("mov.b64 {%0, %1}, %2;" : "=r"(u0), "=r"(u1) : "l"(q));
-    i0 = (int)u0 - 0x4B400000;
-    i1 = (int)u1 - 0x4B400000;
+    i0 = (int)u0;   // 0x4B400000 + q with q in [qmin, qmax] within [0, 255]: the quantized value is the LOW BYTE
+    i1 = (int)u1;
 }
 
-// saturating pack of four integers to u8 (i0 in the low byte) after the clamp to [qmin, qmax].  The byte-wise SIMD
-// min / max intrinsics are emulated on sm_100 (14 instructions per word — a third of the quantizer's issue slots), so
-// the clamp is done on the integers (2 instructions per value), and not at all for the common [0, 255] range where
-// the saturating pack already is the clamp.
+// four quant_int2 results (value in the low byte of each) -> one word, i0 in the low byte: three byte permutes.  (The
+// byte-wise SIMD min / max intrinsics are emulated on sm_100 — 14 instructions per word — and with the tight input clamp
+// neither they nor a saturating pack are needed.)
 template <bool kFull>
-__device__ __forceinline__ uint32_t pack_clamp4(int i0, int i1, int i2, int i3, const QuantParams& p) {
-    if (!kFull) {
-        i0 = min(max(i0, p.ilo), p.ihi);
-        i1 = min(max(i1, p.ilo), p.ihi);
-        i2 = min(max(i2, p.ilo), p.ihi);
-        i3 = min(max(i3, p.ilo), p.ihi);
-    }
-    uint32_t hi16, w;
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi16) : "r"(i3), "r"(i2), "r"(0));
-    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(i1), "r"(i0), "r"(hi16));
-    return w;
+__device__ __forceinline__ uint32_t pack_clamp4(int i0, int i1, int i2, int i3, const QuantParams&) {
+    const uint32_t lo = __byte_perm((uint32_t)i0, (uint32_t)i1, 0x0040), hi = __byte_perm((uint32_t)i2, (uint32_t)i3, 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
 }
 
 // One output word = four channels of one pixel.
