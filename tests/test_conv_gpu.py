@@ -315,3 +315,36 @@ def test_fused_vs_reference_kernel_on_dequantized_input():
                                         torch.zeros(1).cuda(), None, c["stride"], c["pad"])
     assert float(r_acc.abs().max()) < 2 ** 24
     assert torch.equal(acc.float(), r_acc)
+
+
+def test_act_quantize_random_quantizers_match_the_ieee_sequence():
+    """Seeded random (scale, zero, qmin, qmax) — 4 decades of scale, fractional zero points, ranges that do not start at
+    0 — with inputs planted on every rounding boundary and up to 3 ulps either side: the division-free quantizer
+    (tight clamp, packed fp32 pipe, byte-permute packing) equals clamp(round(x / s - z)) computed with IEEE fp32 ops."""
+    import random
+    L = capi.lib()
+    rnd = random.Random(5)
+    N, C, H, W = 2, 64, 16, 32
+    for it in range(60):
+        qmax = rnd.choice([255, 255, 15, 127, 3, 200])
+        qmin = rnd.choice([0, 0, 0, 1, 5]) if qmax > 10 else 0
+        s = 10 ** rnd.uniform(-4, 1.5) * rnd.uniform(1, 2)
+        z = rnd.choice([0.0, -rnd.uniform(0, 300), rnd.uniform(0, 50), -127.5, -0.5])
+        scale = torch.tensor([s], dtype=torch.float32, device="cuda")
+        zero = torch.tensor([z], dtype=torch.float32, device="cuda")
+        g = torch.Generator(device="cuda").manual_seed(it)
+        x = torch.randn(N, C, H, W, device="cuda", generator=g) * (s * (qmax - qmin) * rnd.choice([0.1, 0.5, 2.0]))
+        x = x + (zero + (qmin + qmax) / 2) * scale
+        ks = torch.arange(qmin - 2, min(qmax + 3, qmin + 400), device="cuda", dtype=torch.float32)
+        flat = x.view(-1)
+        for d in range(-3, 4):
+            v = (ks + 0.5 + zero) * scale
+            for _ in range(abs(d)):
+                v = torch.nextafter(v, torch.full_like(v, float("inf") if d > 0 else float("-inf")))
+            flat[(d + 3) * ks.numel():(d + 4) * ks.numel()] = v
+        qmn, qmx = torch.tensor([float(qmin)], device="cuda"), torch.tensor([float(qmax)], device="cuda")
+        aq = capi.ActQuant(scale.data_ptr(), zero.data_ptr(), qmn.data_ptr(), qmx.data_ptr())
+        out = torch.empty(N, H, W, C, dtype=torch.uint8, device="cuda")
+        capi.check(L.qb200_act_quantize_nhwc(x.data_ptr(), N, C, H, W, ctypes.byref(aq), out.data_ptr(), None), "act_quantize")
+        want = torch.clamp(torch.round(x / scale - zero), qmin, qmax).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        assert torch.equal(out, want), (it, s, z, qmin, qmax)
