@@ -17,6 +17,13 @@
 // non-zero activation zero point take the 4-corner prefix-sum path.
 // Persistent: grid = #SMs, static round-robin tile schedule, output-channel tiles fastest so concurrently
 // running CTAs share the same activation slice in L2.
+//
+// Variants of the same kernel: halo (stride-1 R x S kernels with 64 padded channels: one TMA halo
+// load per tile, taps through row-shifted descriptors, tap-major weights), im2col rows (few-channel stems: the A
+// operand is a materialised row matrix), fused quantize (kFQ: fp32 tiles by TMA, eight quantizer warps), residual tail
+// (kRes: identity tensor streamed through per-warp cp.async rings), quantized hand-off (kQ8: the epilogue writes the
+// consumer layer's int8 workspace; kGroups = 2 epilogue groups when that is the only output), ragged channel counts
+// (kRagged).  Each is a template parameter because the epilogue's register budget decides its speed.
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "quant_math.cuh"
