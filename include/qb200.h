@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define QB200_VERSION 101
+#define QB200_VERSION 200
 
 /* error codes (negative; positive values are cudaError_t) */
 #define QB200_OK 0
@@ -226,6 +226,72 @@ int qb200_quantlinear_weightonly(const float* x, int64_t batch, int32_t in_featu
  * torch kernels the reference launches (div, sub, round, clamp, add, mul) — bit-identical to them.  Any range
  * (signed ranges and ranges beyond a byte take an IEEE-division path).  x, out: n fp32 values (may alias). */
 int qb200_fake_quantize_f32(const float* x, int64_t n, const qb200_act_quant* aq, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ops whose activations arrive as a tpack'ed stream
+ * ---------------------------------------------------------------------------------------------- */
+
+/* tpack'ed NCHW activation stream (Quantizer.pack, quantizer.py:228-246, element order of tpack.cu:203-255) ->
+ * NHWC(Cp) bytes holding the STORED values u = q + (sign ? 2^(n_bits-1) : 0), channels C..Cp-1 = 0: the A operand of the
+ * tensor-core conv.  When in_zero / zero_adj are given the kernel also writes *zero_adj = -(offset + *in_zero), the
+ * activation zero point of the integer form of quantconv2d (see qb200_quantconv2d_packed). */
+int qb200_unpack_act_nhwc(const uint8_t* packed, int32_t n_bits, int32_t sign, int32_t N, int32_t C, int32_t H, int32_t W,
+                          uint8_t* q_nhwc, const float* in_zero, float* zero_adj, void* stream);
+
+/* stream -> fp32 with the reference's per-element dequantization (quantconv2d.cu:111-115, quantlinear.cu:110-112):
+ *   q = (sign ? int8 : uint8)(u - offset);   out = plus_zero ? (q + zero[c]) * scale[c] : (q - zero[c]) * scale[c]
+ * c = 0 when n_scale == 1, else (i / inner) % C  (per input channel of an NCHW tensor: inner = H*W). */
+int qb200_dequant_packed_f32(const uint8_t* packed, int32_t n_bits, int32_t sign, int64_t n_elements, int64_t inner, int32_t C,
+                             const float* scale, const float* zero, int32_t n_scale, int32_t plus_zero, float* out,
+                             void* stream);
+
+/* quantconv2d (reference engine/kernels/functions/quantconv2d.cu:49-147 kernel, :164-264 host; funcs.h:113-124) with a
+ * per-tensor input quantizer and symmetric weights, as an integer GEMM on the tensor cores:
+ *   out[n,k,p,q] = in_scale * w_scale[k|0] * ( sum u*qw - (offset + in_zero) * sum_{in-bounds taps} qw ) + bias[k]
+ * = sum (q_in - in_zero) * in_scale * qw * w_scale + bias, the reference's (q - zero) * scale convention on both operands.
+ * s describes the layer (N, C, H, W = the activation tensor the stream encodes); prepared = qb200_conv_prepare_weights.
+ * workspace: qb200_quantconv2d_packed_workspace_bytes(s) bytes.  out_kind QB200_OUT_ACC returns sum u*qw (int32).
+ * Per-input-channel input scales and asymmetric weights do not factor into an integer GEMM: the caller composes
+ * qb200_dequant_packed_f32 + qb200_quantconv2d_weightonly for those (bit-identical to the reference kernel). */
+size_t qb200_quantconv2d_packed_workspace_bytes(const qb200_conv_shape* s);
+int qb200_quantconv2d_packed(const qb200_conv_shape* s, const uint8_t* in_packed, int32_t in_bits, int32_t in_sign,
+                             const float* in_scale, const float* in_zero, const void* prepared, const float* w_scale,
+                             int32_t n_w_scale, const float* bias, void* workspace, void* out, int32_t out_kind, void* stream);
+
+/* quantlinear (reference engine/kernels/functions/quantlinear.cu:39-133 kernel, :231-297 host; funcs.h:37-46):
+ *   out[b,o] = ( sum_k (qi[b,k] + in_zero[b]) * (qw[o,k] + w_zero[o]) * (in_scale[b] * w_scale[o]) ) + bias[o]
+ * fp32, k ascending, each term rounded as the reference kernel rounds it (product, then one FMA with the scale product),
+ * bias added last (0 when NULL, as the reference's wrapper substitutes zeros) — bit-identical to the reference kernel
+ * whenever in_features % 32 == 0 (its shared tiles keep stale entries otherwise).  in_scale / in_zero: batch elements,
+ * w_scale / w_zero: out_features elements (the reference expands 0-d tensors on the host, quantlinear.cu:275-289). */
+int qb200_quantlinear_packed(const uint8_t* in_packed, int32_t in_bits, int32_t in_sign, const float* in_scale,
+                             const float* in_zero, int64_t batch, int32_t in_features, int32_t out_features,
+                             const uint8_t* w_packed, int32_t w_bits, int32_t w_sign, const float* w_scale, const float* w_zero,
+                             const float* bias, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Calibration reductions (reference modelzoo/modules/range/minmax.py:62-108, :44-60, :184-203)
+ * The tensor is viewed as [A][R][B] and reduced over A and B:  per tensor A=1,R=1,B=numel;  weights per channel
+ * A=1,R=K,B=C*R*S;  activations per channel A=N,R=C,B=H*W.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* out_min[r], out_max[r] = the estimator's (xmin, xmax) of row r in ONE pass over x:
+ *   symmetric == 0:  (min x, max x)          symmetric != 0:  (0, max |x|)        (minmax.py:75-77, :89-91)
+ * NaN propagates as in torch.min / torch.max.  update_mode folds the estimator's state update into the same call:
+ *   0  none;   1  run = (min(run_min, xmin), max(run_max, xmax))                          MinMax.update   (:44-60)
+ *   2  run = momentum * x + one_minus_momentum * run, rounded like the torch expression   MAMinMax.update (:184-203)
+ * (modes 1, 2: run_min / run_max hold the previous state, are updated in place, and out_* receive the new state).
+ * workspace: qb200_minmax_workspace_bytes(R) bytes. */
+size_t qb200_minmax_workspace_bytes(int64_t R);
+int qb200_minmax_f32(const float* x, int64_t A, int64_t R, int64_t B, int32_t symmetric, float* out_min, float* out_max,
+                     int32_t update_mode, float momentum, float one_minus_momentum, float* run_min, float* run_max,
+                     void* workspace, void* stream);
+
+/* out[r] = the k-th smallest (1-based; of |x| when use_abs) element of row r — torch.kthvalue's value (minmax.py:78-84,
+ * :92-98), exact (4-pass radix select), NaN sorts last.  1 <= k <= A*B.  workspace: qb200_kthvalue_workspace_bytes(R). */
+size_t qb200_kthvalue_workspace_bytes(int64_t R);
+int qb200_kthvalue_f32(const float* x, int64_t A, int64_t R, int64_t B, int32_t use_abs, int64_t k, float* out, void* workspace,
+                       void* stream);
 
 /* Max pooling over fp32 NCHW planes (planes = N*C), square kernel / stride, -inf padding, floor output size:
  * the op between the stem conv and the first residual stage of the ResNet family (torchvision resnet.py; the reference

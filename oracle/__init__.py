@@ -145,3 +145,78 @@ def quantlinear_float_input(x, w_packed, w_des, w_scale, w_zero, bias):
     lib().qo_quantlinear_float_input(_p(x), _p(w_packed), _p(w_scale), _p(w_zero), int(w_scale.size == 1), n_bits, sign,
                                      None if b is None else _p(b), _p(out), B, in_f, out_f)
     return out
+
+
+def quantconv2d(in_packed, in_des, in_scale, in_zero, w_packed, w_des, w_scale, w_zero, bias, stride, pad):
+    """quantconv2d.cu:49-264 (packed activations x packed weights, (q - zero) * scale on both, sequential fp32)."""
+    n_bits, sign, N, C, H, W = [int(v) for v in np.asarray(in_des)[:6]]
+    wb, ws, K, Cw, R, S = [int(v) for v in np.asarray(w_des)[:6]]
+    assert Cw == C
+    P, Q = conv_out_hw(H, W, R, S, stride, pad)
+    f = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    in_scale, in_zero, w_scale, w_zero = f(in_scale), f(in_zero), f(w_scale), f(w_zero)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    in_packed = np.ascontiguousarray(in_packed, dtype=np.uint8)
+    w_packed = np.ascontiguousarray(w_packed, dtype=np.uint8)
+    out = np.empty((N, K, P, Q), dtype=np.float32)
+    lib().qo_quantconv2d(_p(in_packed), n_bits, sign, _p(in_scale), _p(in_zero), int(in_scale.size == 1), _p(w_packed), wb, ws,
+                         _p(w_scale), _p(w_zero), int(w_scale.size == 1), None if b is None else _p(b), _p(out),
+                         N, C, H, W, K, R, S, stride, pad)
+    return out
+
+
+def quantconv2d_acc(in_packed, in_des, w_packed, w_des, stride, pad):
+    """exact integer accumulators sum(u * qw) over in-bounds taps, u = the stored (offset-binary) activation values."""
+    n_bits, _, N, C, H, W = [int(v) for v in np.asarray(in_des)[:6]]
+    wb, ws, K, Cw, R, S = [int(v) for v in np.asarray(w_des)[:6]]
+    P, Q = conv_out_hw(H, W, R, S, stride, pad)
+    acc = np.empty((N, K, P, Q), dtype=np.int32)
+    lib().qo_quantconv2d_acc(_p(np.ascontiguousarray(in_packed, dtype=np.uint8)), n_bits,
+                             _p(np.ascontiguousarray(w_packed, dtype=np.uint8)), wb, ws, _p(acc), N, C, H, W, K, R, S, stride, pad)
+    return acc
+
+
+def quantlinear(in_packed, in_des, in_scale, in_zero, w_packed, w_des, w_scale, w_zero, bias):
+    """quantlinear.cu:39-133, :231-297 ((q + zero) convention, per-row input scale, sequential fp32)."""
+    ib, isg, B, in_f = [int(v) for v in np.asarray(in_des)[:4]]
+    wb, wsg, out_f, in_w = [int(v) for v in np.asarray(w_des)[:4]]
+    assert in_w == in_f
+    ex = lambda a, n: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32).reshape(-1), (n,)))
+    in_scale, in_zero, w_scale, w_zero = ex(in_scale, B), ex(in_zero, B), ex(w_scale, out_f), ex(w_zero, out_f)
+    b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+    out = np.empty((B, out_f), dtype=np.float32)
+    lib().qo_quantlinear(_p(np.ascontiguousarray(in_packed, dtype=np.uint8)), ib, isg, _p(in_scale), _p(in_zero),
+                         _p(np.ascontiguousarray(w_packed, dtype=np.uint8)), wb, wsg, _p(w_scale), _p(w_zero),
+                         None if b is None else _p(b), _p(out), B, in_f, out_f)
+    return out
+
+
+def _rows(x, granularity, flag):
+    """the estimator's flattened view (range/minmax.py:72-74, :86-88): one row per tensor / channel"""
+    x = np.asarray(x, dtype=np.float32)
+    if granularity == 0:
+        return x.reshape(1, -1)
+    if flag == "activation":
+        x = np.swapaxes(x, 0, 1)
+    return np.ascontiguousarray(x).reshape(x.shape[0], -1)
+
+
+def minmax(x, granularity, flag, symmetric):
+    """range/minmax.py:75-77, :89-91: (xmin, xmax) = (min, max), or (0, max|x|) for symmetric ranges; NaN propagates."""
+    r = _rows(x, granularity, flag)
+    if symmetric:
+        lo, hi = np.zeros(r.shape[0], np.float32), np.abs(r).max(axis=1)
+    else:
+        lo, hi = r.min(axis=1), r.max(axis=1)
+    return (lo[0], hi[0]) if granularity == 0 else (lo, hi)
+
+
+def kthvalue(x, k, granularity, flag, use_abs=False):
+    """range/minmax.py:78-84, :92-98: torch.kthvalue(...)[0] — the k-th smallest (1-based), NaN last."""
+    r = _rows(x, granularity, flag)
+    if use_abs:
+        r = np.abs(r)
+    if not (1 <= k <= r.shape[1]):
+        raise RuntimeError("kthvalue(): selected number k out of range for dimension")
+    v = np.sort(r, axis=1)[:, k - 1]          # numpy sorts NaN last, like torch
+    return v[0] if granularity == 0 else v

@@ -4,7 +4,9 @@ Recipe (no reference build system is run; the sources are compiled where they li
   nvcc  /root/reference/engine/kernels/tpack/tpack.cu
   nvcc  /root/reference/engine/kernels/functions/quantconv2d_float_input.cu
   nvcc  /root/reference/engine/kernels/functions/quantlinear_float_input.cu
-  g++   oracle/ref_bind.cpp   (our own 4-op pybind shim, includes the reference headers)
+  nvcc  /root/reference/engine/kernels/functions/quantconv2d.cu
+  nvcc  /root/reference/engine/kernels/functions/quantlinear.cu
+  g++   oracle/ref_bind.cpp   (our own 6-op pybind shim, includes the reference headers)
   link  -> oracle/_ref/quant_engine_ref.so   (git-ignored; travels to the GPU box with gpurun)
 
 The reference tpack/tunpack have a CPU path (tpack.cu:140-190, :371-419) so they run in the CPU
@@ -41,7 +43,9 @@ def available():
 
 def build(force=False):
     so = os.path.join(OUT, NAME + ".so")
-    if os.path.exists(so) and not force:
+    shim = os.path.join(HERE, "ref_bind.cpp")
+    stale = os.path.exists(so) and os.path.isdir(KERN) and max(os.path.getmtime(shim), os.path.getmtime(__file__)) > os.path.getmtime(so)
+    if os.path.exists(so) and not force and not stale:
         return so
     if not os.path.isdir(KERN):
         raise FileNotFoundError(f"reference sources not present at {KERN}; oracle/_ref must be prebuilt")
@@ -52,27 +56,22 @@ def build(force=False):
             "-D__CUDA_NO_HALF_OPERATORS__", "-D__CUDA_NO_HALF_CONVERSIONS__",
             "-D__CUDA_NO_BFLOAT16_CONVERSIONS__", "-D__CUDA_NO_HALF2_OPERATORS__"] + inc + defs
     gxx = ["g++", "-O2", "-std=c++17", "-fPIC"] + inc + defs
-    jobs = [
-        (nvcc + ["-c", os.path.join(KERN, "tpack", "tpack.cu"), "-o", os.path.join(OUT, "tpack.o")]),
-        (nvcc + ["-c", os.path.join(KERN, "functions", "quantconv2d_float_input.cu"),
-                 "-o", os.path.join(OUT, "quantconv2d_float_input.o")]),
-        (nvcc + ["-c", os.path.join(KERN, "functions", "quantlinear_float_input.cu"),
-                 "-o", os.path.join(OUT, "quantlinear_float_input.o")]),
-        (gxx + ["-c", os.path.join(HERE, "ref_bind.cpp"), "-o", os.path.join(OUT, "ref_bind.o")]),
-    ]
-    with ThreadPoolExecutor(4) as ex:
+    funcs = ["quantconv2d_float_input", "quantlinear_float_input", "quantconv2d", "quantlinear"]
+    jobs = [(nvcc + ["-c", os.path.join(KERN, "tpack", "tpack.cu"), "-o", os.path.join(OUT, "tpack.o")])]
+    jobs += [(nvcc + ["-c", os.path.join(KERN, "functions", f + ".cu"), "-o", os.path.join(OUT, f + ".o")]) for f in funcs]
+    jobs += [(gxx + ["-c", os.path.join(HERE, "ref_bind.cpp"), "-o", os.path.join(OUT, "ref_bind.o")])]
+    with ThreadPoolExecutor(6) as ex:
         for r in ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), jobs):
             if r.returncode != 0:
                 raise RuntimeError("reference build failed:\n" + r.stderr[-4000:])
-    link = ["g++", "-shared", "-o", so,
-            os.path.join(OUT, "tpack.o"), os.path.join(OUT, "quantconv2d_float_input.o"),
-            os.path.join(OUT, "quantlinear_float_input.o"), os.path.join(OUT, "ref_bind.o"),
+    objs = ["tpack.o"] + [f + ".o" for f in funcs] + ["ref_bind.o"]
+    link = ["g++", "-shared", "-o", so] + [os.path.join(OUT, o) for o in objs] + [
             f"-L{libdir}", "-L/usr/local/cuda/lib64", "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python",
             "-lc10_cuda", "-ltorch_cuda", "-lcudart", f"-Wl,-rpath,{libdir}"]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference link failed:\n" + r.stderr[-4000:])
-    for o in ("tpack.o", "quantconv2d_float_input.o", "quantlinear_float_input.o", "ref_bind.o"):
+    for o in objs:
         os.remove(os.path.join(OUT, o))
     return so
 

@@ -202,3 +202,106 @@ void qo_quantlinear_float_input(const float* x, const uint8_t* w_packed, const f
             out[(int64_t)b * out_f + o] = acc + (bias ? bias[o] : 0.0f);          /* :104 */
         }
 }
+
+/* ---- engine/kernels/functions/quantconv2d.cu:49-147: packed activations x packed weights ---------------
+ * Both operands are tpack streams; each MAC dequantizes both with (q - zero) * scale (:113-115, :127-129) and
+ * accumulates in fp32 in the order inc -> keh -> kew, bias first (:95-134; `+= a * b` contracted to FFMA by nvcc). */
+static inline uint8_t qo_stream_get(const uint8_t* s, int64_t e, int n_bits)
+{
+    const uint8_t mask = (uint8_t)((1 << n_bits) - 1);
+    const int64_t byte = e * n_bits / 8;
+    const int bit = (int)(e * n_bits % 8);
+    uint8_t v = (uint8_t)((s[byte] >> bit) & mask);
+    if (bit + n_bits > 8) v |= (uint8_t)((s[byte + 1] << (8 - bit)) & mask);
+    return v;
+}
+
+void qo_quantconv2d(const uint8_t* in_packed, int in_bits, int in_sign, const float* in_scale, const float* in_zero,
+                    int in_per_tensor, const uint8_t* w_packed, int w_bits, int w_sign, const float* w_scale,
+                    const float* w_zero, int w_per_tensor, const float* bias, float* out,
+                    int N, int C, int H, int W, int K, int R, int S, int stride, int pad)
+{
+    const int P = (H + 2 * pad - R) / stride + 1;                       /* :219 */
+    const int Q = (W + 2 * pad - S) / stride + 1;                       /* :220 */
+    const uint8_t ioff = in_sign ? (uint8_t)(1 << (in_bits - 1)) : 0;   /* :227 */
+    const uint8_t woff = w_sign ? (uint8_t)(1 << (w_bits - 1)) : 0;     /* :228 */
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k)
+            for (int p = 0; p < P; ++p)
+                for (int q = 0; q < Q; ++q) {
+                    float o = bias ? bias[k] : 0.0f;                                              /* :92 */
+                    for (int c = 0; c < C; ++c)
+                        for (int r = 0; r < R; ++r)
+                            for (int s = 0; s < S; ++s) {
+                                const int ih = p * stride + r - pad, iw = q * stride + s - pad;   /* :98-99 */
+                                if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;             /* :101 */
+                                uint8_t a = qo_stream_get(in_packed, (((int64_t)n * C + c) * H + ih) * W + iw, in_bits);
+                                a = (uint8_t)(a - ioff);                                          /* :111 */
+                                const float af = in_sign ? (float)(int8_t)a : (float)a;           /* :112 */
+                                const float xf = in_per_tensor ? (af - in_zero[0]) * in_scale[0]
+                                                               : (af - in_zero[c]) * in_scale[c]; /* :113-115 */
+                                uint8_t w = qo_stream_get(w_packed, (((int64_t)k * C + c) * R + r) * S + s, w_bits);
+                                w = (uint8_t)(w - woff);                                          /* :125 */
+                                const float wv = w_sign ? (float)(int8_t)w : (float)w;            /* :126 */
+                                const float wf = w_per_tensor ? (wv - w_zero[0]) * w_scale[0]
+                                                              : (wv - w_zero[k]) * w_scale[k];    /* :127-129 */
+                                o = fmaf(xf, wf, o);                                              /* :132 */
+                            }
+                    out[(((int64_t)n * K + k) * P + p) * Q + q] = o;                              /* :139 */
+                }
+}
+
+/* integer accumulators of the same op: sum of STORED activation values (u = q + offset) times signed weights over the
+ * in-bounds taps — what the tensor-core path accumulates before its epilogue folds -(offset + zero) * sum(qw) in */
+void qo_quantconv2d_acc(const uint8_t* in_packed, int in_bits, const uint8_t* w_packed, int w_bits, int w_sign, int32_t* acc,
+                        int N, int C, int H, int W, int K, int R, int S, int stride, int pad)
+{
+    const int P = (H + 2 * pad - R) / stride + 1, Q = (W + 2 * pad - S) / stride + 1;
+    const uint8_t woff = w_sign ? (uint8_t)(1 << (w_bits - 1)) : 0;
+#pragma omp parallel for collapse(2)
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k)
+            for (int p = 0; p < P; ++p)
+                for (int q = 0; q < Q; ++q) {
+                    int32_t o = 0;
+                    for (int c = 0; c < C; ++c)
+                        for (int r = 0; r < R; ++r)
+                            for (int s = 0; s < S; ++s) {
+                                const int ih = p * stride + r - pad, iw = q * stride + s - pad;
+                                if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+                                const int32_t u = qo_stream_get(in_packed, (((int64_t)n * C + c) * H + ih) * W + iw, in_bits);
+                                const uint8_t w = (uint8_t)(qo_stream_get(w_packed, (((int64_t)k * C + c) * R + r) * S + s, w_bits) - woff);
+                                o += u * (w_sign ? (int32_t)(int8_t)w : (int32_t)w);
+                            }
+                    acc[(((int64_t)n * K + k) * P + p) * Q + q] = o;
+                }
+}
+
+/* ---- engine/kernels/functions/quantlinear.cu:39-133: packed x packed linear ----------------------------
+ * tmp += (qi + in_zero[row]) * (qw + w_zero[col]) * (in_scale[row] * w_scale[col]) for k ascending (:110-120: the product
+ * of the two operands is rounded, then multiplied by the scale product and added — nvcc contracts that last multiply-add
+ * to one FFMA), out = tmp + bias (:127).  Sums exactly input_size terms (the reference's 32-wide tiles multiply stale
+ * entries when input_size % 32 != 0, see qo_quantlinear_float_input). */
+void qo_quantlinear(const uint8_t* in_packed, int in_bits, int in_sign, const float* in_scale, const float* in_zero,
+                    const uint8_t* w_packed, int w_bits, int w_sign, const float* w_scale, const float* w_zero,
+                    const float* bias, float* out, int batch, int in_f, int out_f)
+{
+    const uint8_t ioff = in_sign ? (uint8_t)(1 << (in_bits - 1)) : 0;
+    const uint8_t woff = w_sign ? (uint8_t)(1 << (w_bits - 1)) : 0;
+#pragma omp parallel for collapse(2)
+    for (int b = 0; b < batch; ++b)
+        for (int o = 0; o < out_f; ++o) {
+            float tmp = 0.0f;                                                               /* :79 */
+            const float sc = in_scale[b] * w_scale[o];                                      /* :96 */
+            for (int k = 0; k < in_f; ++k) {
+                const uint8_t a = (uint8_t)(qo_stream_get(in_packed, (int64_t)b * in_f + k, in_bits) - ioff);   /* :110 */
+                const float av = (in_sign ? (float)(int8_t)a : (float)a) + in_zero[b];      /* :111-112 */
+                const uint8_t w = (uint8_t)(qo_stream_get(w_packed, (int64_t)o * in_f + k, w_bits) - woff);     /* :115 */
+                const float wv = (w_sign ? (float)(int8_t)w : (float)w) + w_zero[o];        /* :116-117 */
+                const float prod = av * wv;
+                tmp = fmaf(prod, sc, tmp);                                                  /* :120 */
+            }
+            out[(int64_t)b * out_f + o] = tmp + (bias ? bias[o] : 0.0f);                    /* :127 */
+        }
+}

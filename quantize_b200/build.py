@@ -22,7 +22,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libqb200.so")
 EXT = os.path.join(HERE, "quant_engine.so")
 
-CU_SOURCES = ["common.cu", "pack.cu", "actquant.cu", "wprep.cu", "conv_direct.cu", "conv_umma.cu", "conv_dw.cu", "conv_api.cu", "pool.cu"]
+CU_SOURCES = ["common.cu", "pack.cu", "actquant.cu", "wprep.cu", "conv_direct.cu", "conv_umma.cu", "conv_dw.cu", "conv_api.cu", "pool.cu", "packed_ops.cu", "calib.cu"]
 HEADERS = ["common.cuh", "conv_common.cuh", "quant_math.cuh", os.path.join(ROOT, "include", "qb200.h")]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
@@ -87,7 +87,7 @@ def build_ext(force=False):
     from torch.utils import cpp_extension as ce
     os.makedirs(BUILD, exist_ok=True)
     src = os.path.join(CSRC, "pybind.cpp")
-    digest = _digest([src, os.path.join(ROOT, "include", "qb200.h")], torch.__version__)
+    digest = _digest([src, os.path.join(ROOT, "include", "qb200.h")], torch.__version__ + " rpath=$ORIGIN:$ORIGIN/quantize_b200")
     if not force and not _stale(EXT, "ext.stamp", digest):
         return EXT
     inc = [f"-I{p}" for p in ce.include_paths()] + [f"-I{sysconfig.get_paths()['include']}",
@@ -99,14 +99,32 @@ def build_ext(force=False):
     _run(["g++", "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden"] + inc + defs + ["-c", src, "-o", obj])
     _run(["g++", "-shared", "-o", EXT, obj, f"-L{HERE}", "-lqb200", f"-L{libdir}", "-L/usr/local/cuda/lib64",
           "-lc10", "-ltorch", "-ltorch_cpu", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda", "-lcudart",
-          "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{libdir}"])
+          "-Wl,-rpath,$ORIGIN:$ORIGIN/quantize_b200", f"-Wl,-rpath,{libdir}"])
     _write_stamp("ext.stamp", digest)
     return EXT
+
+
+def top_level_name():
+    """file name of the extension as a top-level module: quant_engine.<abi tag>.so"""
+    return "quant_engine" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so")
+
+
+def install_top_level(dst=None):
+    """Copy quant_engine.so to `dst` (default: the repository root) as the TOP-LEVEL module `quant_engine`, the name the
+    reference imports (engine/__init__.py:1-5: `from quant_engine import *`).  Its rpath also lists
+    $ORIGIN/quantize_b200, so it finds libqb200.so inside the package directory beside it."""
+    import shutil
+    dst = dst or os.path.join(ROOT, top_level_name())
+    os.makedirs(os.path.dirname(dst), exist_ok=True)
+    if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(EXT) or os.path.getsize(dst) != os.path.getsize(EXT):
+        shutil.copy2(EXT, dst)
+    return dst
 
 
 def build_all(force=False, verbose=False):
     build_lib(force=force, verbose=verbose)
     build_ext(force=force)
+    install_top_level()
 
 
 if __name__ == "__main__":

@@ -18,6 +18,9 @@ SYMBOLS = [
     "qb200_quantconv2d_fused", "qb200_conv2d_q8_nhwc", "qb200_quantconv2d_weightonly",
     "qb200_conv_quantize_input", "qb200_conv_from_workspace", "qb200_conv_is_single_kernel", "qb200_watchdog_code",
     "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_quantlinear_weightonly", "qb200_fake_quantize_f32",
+    "qb200_unpack_act_nhwc", "qb200_dequant_packed_f32", "qb200_quantconv2d_packed", "qb200_quantconv2d_packed_workspace_bytes",
+    "qb200_quantlinear_packed", "qb200_minmax_f32", "qb200_minmax_workspace_bytes", "qb200_kthvalue_f32",
+    "qb200_kthvalue_workspace_bytes",
 ]
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
@@ -88,6 +91,19 @@ def lib():
         L.qb200_maxpool2d_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp]
         L.qb200_fake_quantize_f32.argtypes = [vp, i64, ap, vp, vp]
         L.qb200_quantlinear_weightonly.argtypes = [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp]
+        f32 = ctypes.c_float
+        L.qb200_unpack_act_nhwc.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.qb200_dequant_packed_f32.argtypes = [vp, i32, i32, i64, i64, i32, vp, vp, i32, i32, vp, vp]
+        L.qb200_quantconv2d_packed_workspace_bytes.argtypes = [sp]
+        L.qb200_quantconv2d_packed_workspace_bytes.restype = ctypes.c_size_t
+        L.qb200_quantconv2d_packed.argtypes = [sp, vp, i32, i32, vp, vp, vp, vp, i32, vp, vp, vp, i32, vp]
+        L.qb200_quantlinear_packed.argtypes = [vp, i32, i32, vp, vp, i64, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]
+        L.qb200_minmax_workspace_bytes.argtypes = [i64]
+        L.qb200_minmax_workspace_bytes.restype = ctypes.c_size_t
+        L.qb200_minmax_f32.argtypes = [vp, i64, i64, i64, i32, vp, vp, i32, f32, f32, vp, vp, vp, vp]
+        L.qb200_kthvalue_workspace_bytes.argtypes = [i64]
+        L.qb200_kthvalue_workspace_bytes.restype = ctypes.c_size_t
+        L.qb200_kthvalue_f32.argtypes = [vp, i64, i64, i64, i32, i64, vp, vp, vp]
         _lib = L
     return _lib
 

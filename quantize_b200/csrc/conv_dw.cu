@@ -69,18 +69,21 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
             for (int i0 = 0; i0 < in_h * in_w; i0 += 128) {
                 float v[4];
                 int off[4];
+                bool inb[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int i = i0 + u * 32 + lane;
                     const int r = (int)(((uint32_t)i * magic_in) >> 16), col = i - r * in_w;
                     const int ih = ih0 + r, iw = iw0 + col;
-                    const bool in = i < in_h * in_w && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+                    inb[u] = i < in_h * in_w && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
                     off[u] = i < in_h * in_w ? r * in_w_alloc + col : -1;
-                    v[u] = in ? __ldg(xc + ih * g.W + iw) : __int_as_float(0x7fc00000);
+                    v[u] = inb[u] ? __ldg(xc + ih * g.W + iw) : 0.f;
                 }
+                // pixels outside the image are 0 (padded taps add nothing); an in-image NaN goes through the quantizer
+                // like everywhere else in the engine (-> qmin)
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (off[u] >= 0) pch[off[u]] = (v[u] == v[u]) ? quant1(v[u]) : (uint8_t)0;   // NaN marks "outside"
+                    if (off[u] >= 0) pch[off[u]] = inb[u] ? quant1(v[u]) : (uint8_t)0;
             }
         }
     } else {

@@ -32,6 +32,7 @@
 #include <cstdint>
 #include <climits>
 
+#include <atomic>
 #include <type_traits>
 
 namespace qb200 {
@@ -667,7 +668,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (kQ8 && ep.q8_out != nullptr) q8p = load_params(ep.q8_scale, ep.q8_zero, ep.q8_qmin, ep.q8_qmax);
         // int8-only output: relu(v) followed by the quantizer's clamp to [xlo, xhi] is one clamp to [max(xlo, 0), xhi]
         // (a NaN ends at the lower bound either way), so the separate ReLU is dropped
-        const bool relu_folded = kQ8 && !kRes && ep.q8_out != nullptr && !ep.store_f32 && ep.relu != 0;
+        // (only the branch-free quantizer applies xlo; quant_word_exact — ranges outside a byte — keeps the explicit ReLU)
+        const bool relu_folded = kQ8 && !kRes && ep.q8_out != nullptr && !ep.store_f32 && ep.relu != 0 && q8p.byte_clamp != 0;
         if (relu_folded) q8p.xlo = fmaxf(q8p.xlo, 0.f);
         const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
         // ---- residual stream (fused tail) ----
@@ -1303,7 +1305,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
 
     const size_t smem = (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + (fq ? prm.x_stages * xb : 0) +
                         1024 /*align*/ + tail;
-    static thread_local bool smem_set = false;
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a function: one flag per device (a thread
+    // that moves from cuda:0 to cuda:1 must set it again; setting it twice from racing threads is harmless)
+    static std::atomic<uint64_t> smem_set_mask{0};
+    int cur_dev = 0;
+    QB_CUDA(cudaGetDevice(&cur_dev));
+    const bool smem_set = cur_dev >= 0 && cur_dev < 64 && ((smem_set_mask.load(std::memory_order_acquire) >> cur_dev) & 1ull);
     if (!smem_set) {
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
@@ -1312,7 +1319,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
-        smem_set = true;
+        if (cur_dev >= 0 && cur_dev < 64) smem_set_mask.fetch_or(1ull << cur_dev, std::memory_order_release);
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
     const int grid = total_tiles < sms ? total_tiles : sms;

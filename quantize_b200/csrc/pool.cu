@@ -5,6 +5,7 @@
 // Results are bit-identical to torch.nn.functional.max_pool2d (max is exact; padding behaves as -inf).
 #include <algorithm>
 #include <cfloat>
+#include <atomic>
 #include "common.cuh"
 
 namespace qb200 {
@@ -121,8 +122,18 @@ extern "C" int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, in
     const int in_rows = std::min(H, (band_rows - 1) * stride + kernel);
     const size_t smem = ((size_t)in_rows + band_rows) * W * 4;  // staged input rows + one column-reduced row per output row
     QB_REQUIRE(planes * bands < (1ll << 31), QB200_EINVAL, "maxpool2d: too many blocks");
+    // the shared-memory attribute is per (function, device): set it once for every instantiation on each device
+    static std::atomic<uint64_t> attr_mask{0};
+    int dev = 0;
+    QB_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !((attr_mask.load(std::memory_order_acquire) >> dev) & 1ull)) {
+        QB_CUDA(cudaFuncSetAttribute(maxpool2d_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        QB_CUDA(cudaFuncSetAttribute(maxpool2d_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        QB_CUDA(cudaFuncSetAttribute(maxpool2d_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        QB_CUDA(cudaFuncSetAttribute(maxpool2d_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        if (dev >= 0 && dev < 64) attr_mask.fetch_or(1ull << dev, std::memory_order_release);
+    }
     auto launch = [&](auto kern) -> int {
-        QB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         QB_CUDA(launch_pdl(kern, dim3((unsigned)(planes * bands)), dim3(kPoolThreads), smem, static_cast<cudaStream_t>(stream),
                            x, out, H, W, P, Q, kernel, stride, pad, band_rows, bands, in_rows));
         return 0;

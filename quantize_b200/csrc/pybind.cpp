@@ -15,12 +15,18 @@
 // the op runs the fused activation-quantize + int8 tensor-core path; without them it computes the reference's
 // weight-only fp32 semantic.  residual / fuse_relu fuse `relu(out + residual)` into the epilogue (bit-identical to the
 // separate torch ops) for callers that own the surrounding block.
+//
+// Threading: Python objects are converted while the GIL is held; everything after that — cache lookups,
+// allocation, the C-ABI launches — runs with the GIL RELEASED.  g_mu guards only the derived-operand caches (short
+// critical sections; no code holding it ever takes the GIL).  Launches go to the current stream of the input's device.
 #include <pybind11/pybind11.h>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
+#include <ATen/cuda/CUDAEvent.h>
 #include <c10/cuda/CUDAGuard.h>
 
 #include <list>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 
@@ -126,22 +132,24 @@ struct Key {
     const void* ptr;
     uint64_t version;
     const void* aux;
-    bool operator==(const Key& o) const { return ptr == o.ptr && version == o.version && aux == o.aux; }
+    uint64_t aux2;
+    bool operator==(const Key& o) const { return ptr == o.ptr && version == o.version && aux == o.aux && aux2 == o.aux2; }
 };
 struct KeyHash {
     size_t operator()(const Key& k) const {
         return std::hash<const void*>()(k.ptr) ^ (std::hash<uint64_t>()(k.version) * 1000003u) ^
-               (std::hash<const void*>()(k.aux) << 1);
+               (std::hash<const void*>()(k.aux) << 1) ^ (std::hash<uint64_t>()(k.aux2) * 0x9E3779B97F4A7C15ull);
     }
 };
 
 // An entry is valid only while the storage it was derived from is alive (a freed block can be handed out again
-// at the same address), so every entry keeps a weak reference to that storage.
+// at the same address), so every entry keeps a weak reference to that storage.  Values are shared_ptrs: a caller keeps
+// its value alive after the lock is dropped even if another thread evicts the entry.
 template <typename V>
 class DerivedCache {
   public:
     explicit DerivedCache(size_t cap) : cap_(cap) {}
-    V* find(const Key& k, const at::Tensor& src) {
+    std::shared_ptr<V> find(const Key& k, const at::Tensor& src) {
         auto it = map_.find(k);
         if (it == map_.end()) return nullptr;
         auto live = it->second->weak.lock();
@@ -151,23 +159,29 @@ class DerivedCache {
             return nullptr;
         }
         order_.splice(order_.begin(), order_, it->second);
-        return &it->second->value;
+        return it->second->value;
     }
-    V* insert(const Key& k, const at::Tensor& src, V v) {
-        order_.push_front(Entry{k, c10::weak_intrusive_ptr<c10::StorageImpl>(src.storage().getWeakStorageImpl()), std::move(v)});
+    std::shared_ptr<V> insert(const Key& k, const at::Tensor& src, V v) {
+        auto old = map_.find(k);
+        if (old != map_.end()) {
+            order_.erase(old->second);
+            map_.erase(old);
+        }
+        order_.push_front(Entry{k, c10::weak_intrusive_ptr<c10::StorageImpl>(src.storage().getWeakStorageImpl()),
+                                std::make_shared<V>(std::move(v))});
         map_[k] = order_.begin();
         while (order_.size() > cap_) {
             map_.erase(order_.back().key);
             order_.pop_back();
         }
-        return &order_.front().value;
+        return order_.front().value;
     }
 
   private:
     struct Entry {
         Key key;
         c10::weak_intrusive_ptr<c10::StorageImpl> weak;
-        V value;
+        std::shared_ptr<V> value;
     };
     size_t cap_;
     std::list<Entry> order_;
@@ -177,93 +191,164 @@ class DerivedCache {
 struct PreparedWeights {
     at::Tensor buffer;
     bool zero_is_zero;
+    // the buffer is written on the stream of the first call; other streams wait on this event before reading it
+    std::shared_ptr<at::cuda::CUDAEvent> ready;
+    cudaStream_t stream;
 };
 
-std::mutex g_mu;
+std::mutex g_mu;   // guards the four caches below, nothing else
 DerivedCache<std::vector<int64_t>> g_des_cache(4096);
 DerivedCache<PreparedWeights> g_prep_cache(2048);
 DerivedCache<at::Tensor> g_float_cache(4096);
+DerivedCache<std::pair<float, float>> g_range_cache(4096);
 
-Key key_of(const at::Tensor& t, const void* aux = nullptr) { return Key{t.data_ptr(), (uint64_t)t._version(), aux}; }
+// Tensor::_version() throws for inference-mode tensors (torch.inference_mode()): they cannot be modified in place
+// outside inference mode, so the address alone identifies them.
+uint64_t version_of(const at::Tensor& t) { return t.is_inference() ? 0ull : (uint64_t)t._version(); }
+Key key_of(const at::Tensor& t, const void* aux = nullptr, uint64_t aux2 = 0) { return Key{t.data_ptr(), version_of(t), aux, aux2}; }
 
-const std::vector<int64_t>& host_des(const at::Tensor& des) {
+std::shared_ptr<std::vector<int64_t>> host_des(const at::Tensor& des) {
     const Key k = key_of(des);
-    if (auto* v = g_des_cache.find(k, des)) return *v;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        if (auto v = g_des_cache.find(k, des)) return v;
+    }
     auto dh = des.to(at::kCPU, at::kLong).contiguous();  // one blocking copy per descriptor (the reference: 6 per call)
     std::vector<int64_t> v(dh.data_ptr<int64_t>(), dh.data_ptr<int64_t>() + dh.numel());
-    return *g_des_cache.insert(k, des, std::move(v));
+    std::lock_guard<std::mutex> lock(g_mu);
+    return g_des_cache.insert(k, des, std::move(v));
 }
 
-// scale / zero / qmin / qmax as a device float pointer without per-call work
-const float* device_float(const py::object& o, const at::Device& dev, std::vector<at::Tensor>& keep, const char* name) {
+// A quantizer parameter as Python hands it over (tensor with one element, or a number), converted under the GIL.
+struct QParam {
+    bool none = true, is_tensor = false;
     at::Tensor t;
+    double val = 0.0;
+};
+QParam qparam(const py::object& o, const char* name) {
+    QParam q;
+    if (o.is_none()) return q;
+    q.none = false;
     if (THPVariable_Check(o.ptr())) {
-        t = THPVariable_Unpack(o.ptr());
-        TORCH_CHECK(t.numel() == 1, name, " must have exactly one element (per-tensor activation quantization)");
+        q.is_tensor = true;
+        q.t = THPVariable_Unpack(o.ptr());
+        TORCH_CHECK(q.t.numel() == 1, name, " must have exactly one element (per-tensor activation quantization)");
+    } else {
+        q.val = o.cast<double>();
+    }
+    return q;
+}
+
+// scale / zero / qmin / qmax as a device float pointer without per-call work (no GIL needed)
+const float* device_float(const QParam& q, const at::Device& dev, std::vector<at::Tensor>& keep) {
+    if (q.is_tensor) {
+        const at::Tensor& t = q.t;
         if (t.device() == dev && t.scalar_type() == at::kFloat && t.is_contiguous()) {
             keep.push_back(t);
             return t.data_ptr<float>();
         }
         const Key k = key_of(t, reinterpret_cast<const void*>((intptr_t)dev.index() + 1));
-        if (auto* v = g_float_cache.find(k, t)) return v->data_ptr<float>();
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            if (auto v = g_float_cache.find(k, t)) { keep.push_back(*v); return v->data_ptr<float>(); }
+        }
         auto f = t.detach().to(dev, at::kFloat).contiguous();
-        return g_float_cache.insert(k, t, f)->data_ptr<float>();
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto v = g_float_cache.insert(k, t, f);
+        keep.push_back(*v);
+        return v->data_ptr<float>();
     }
     // python number: one cached device scalar per (value, device)
     static std::unordered_map<int64_t, at::Tensor> scalars;
-    const double val = o.cast<double>();
-    float fv = (float)val;
+    float fv = (float)q.val;
     int32_t bits;
     memcpy(&bits, &fv, 4);
     const int64_t sk = ((int64_t)dev.index() << 32) | (uint32_t)bits;
-    auto it = scalars.find(sk);
-    if (it == scalars.end()) it = scalars.emplace(sk, at::full({1}, val, at::TensorOptions().dtype(at::kFloat).device(dev))).first;
-    return it->second.data_ptr<float>();
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        auto it = scalars.find(sk);
+        if (it != scalars.end()) return it->second.data_ptr<float>();
+    }
+    auto fresh = at::full({1}, q.val, at::TensorOptions().dtype(at::kFloat).device(dev));
+    std::lock_guard<std::mutex> lock(g_mu);
+    return scalars.emplace(sk, fresh).first->second.data_ptr<float>();
+}
+
+// The integer path stores activations as unsigned bytes and feeds the MMA an unsigned A operand: it needs
+// 0 <= qmin <= qmax <= 255.  Other ranges (signed symmetric activation quantizers: qmin = -2^(n-1), minmax.py:124-127; an
+// uncalibrated Quantizer's default buffers) take the fake-quantize + fp32 path.  Tensors are read once per (ptr, version).
+bool activation_range_fits_u8(const QParam& qmin, const QParam& qmax) {
+    auto value = [](const QParam& q) -> float {
+        if (!q.is_tensor) return (float)q.val;
+        return q.t.detach().to(at::kCPU, at::kFloat).item<float>();
+    };
+    float lo, hi;
+    if (qmin.is_tensor || qmax.is_tensor) {
+        const at::Tensor& anchor = qmin.is_tensor ? qmin.t : qmax.t;
+        const Key k = key_of(anchor, qmax.is_tensor ? qmax.t.data_ptr() : nullptr, qmax.is_tensor ? version_of(qmax.t) : 0);
+        std::shared_ptr<std::pair<float, float>> v;
+        {
+            std::lock_guard<std::mutex> lock(g_mu);
+            v = g_range_cache.find(k, anchor);
+        }
+        if (!v) {
+            std::pair<float, float> r(value(qmin), value(qmax));   // one sync per quantizer
+            std::lock_guard<std::mutex> lock(g_mu);
+            v = g_range_cache.insert(k, anchor, r);
+        }
+        lo = v->first;
+        hi = v->second;
+    } else {
+        lo = (float)qmin.val;
+        hi = (float)qmax.val;
+    }
+    return lo >= 0.f && hi <= 255.f && lo <= hi;
+}
+
+// prepared weights: derived once per (weight storage, version, descriptor, weight_zero storage + version, groups)
+std::shared_ptr<PreparedWeights> prepared_weights(const qb200_conv_shape& s, const at::Tensor& weight, const at::Tensor& weight_des,
+                                                  const at::Tensor& weight_zero, void* st) {
+    const uint64_t aux2 = (uint64_t)reinterpret_cast<uintptr_t>(weight_zero.data_ptr()) * 31u + version_of(weight_zero) * 1000003u +
+                          (uint64_t)(s.C / (s.Cg > 0 ? s.Cg : 1));
+    const Key wk = key_of(weight, weight_des.data_ptr(), aux2);
+    std::shared_ptr<PreparedWeights> pw;
+    {
+        std::lock_guard<std::mutex> lock(g_mu);
+        pw = g_prep_cache.find(wk, weight);
+    }
+    if (!pw) {
+        PreparedWeights fresh;
+        fresh.buffer = at::empty({(int64_t)qb200_conv_prepared_bytes(&s)}, weight.options());
+        check_rc(qb200_conv_prepare_weights(&s, weight.data_ptr<uint8_t>(), fresh.buffer.data_ptr(), st), "prepare_weights");
+        fresh.ready = std::make_shared<at::cuda::CUDAEvent>();
+        fresh.ready->record(at::cuda::getCurrentCUDAStream());
+        fresh.stream = static_cast<cudaStream_t>(st);
+        fresh.zero_is_zero = weight_zero.abs().max().item<float>() == 0.f;  // one sync per weight tensor
+        std::lock_guard<std::mutex> lock(g_mu);
+        pw = g_prep_cache.insert(wk, weight, std::move(fresh));
+    }
+    if (pw->stream != static_cast<cudaStream_t>(st)) pw->ready->block(at::cuda::getCurrentCUDAStream());
+    return pw;
+}
+
+// Quantizer.simulate on the device for the fp32 fall-backs (any range): one engine kernel
+at::Tensor fake_quantize_dev(const at::Tensor& input, const qb200_act_quant& aq, void* st) {
+    auto out = at::empty_like(input);
+    check_rc(qb200_fake_quantize_f32(input.data_ptr<float>(), input.numel(), &aq, out.data_ptr<float>(), st), "fake_quantize");
+    return out;
 }
 
 // ------------------------------------------------------------------------------------------------
 // quantconv2d_float_input
 // ------------------------------------------------------------------------------------------------
+struct QuantArgs {
+    QParam scale, zero, qmin, qmax;
+};
+
+// (GIL released, device guard set) d = [n_bits, sign, K, Cg, R, S]; input is 4-D
 at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des, const std::vector<int64_t>& d,
                      const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias,
-                     const int stride, const int padding, const py::object& input_scale, const py::object& input_zero,
-                     const py::object& input_qmin, const py::object& input_qmax, const c10::optional<at::Tensor>& residual,
-                     const bool fuse_relu);
-
-at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des,
-                                   const at::Tensor& weight_scale, const at::Tensor& weight_zero,
-                                   const c10::optional<at::Tensor>& bias, const int stride, const int padding,
-                                   const py::object& input_scale, const py::object& input_zero,
-                                   const py::object& input_qmin, const py::object& input_qmax,
-                                   const c10::optional<at::Tensor>& residual, const bool fuse_relu) {
-    // same checks, same messages as quantconv2d_float_input.cu:151-159
-    CHECK_INPUT(input);
-    CHECK_FLOAT(input);
-    CHECK_INPUT(weight);
-    CHECK_INPUT(weight_des);
-    CHECK_INPUT(weight_scale);
-    CHECK_INPUT(weight_zero);
-    if (bias.has_value()) { CHECK_INPUT(bias.value()); }
-    TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
-    TORCH_CHECK(weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
-    CHECK_FLOAT(weight_scale);
-    CHECK_FLOAT(weight_zero);
-    if (bias.has_value()) { TORCH_CHECK(bias.value().dtype() == torch::kFloat32, "bias must be a float tensor"); }
-
-    c10::cuda::CUDAGuard guard(input.device());
-    std::lock_guard<std::mutex> lock(g_mu);
-
-    const std::vector<int64_t>& d = host_des(weight_des);
-    TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
-    return conv_core(input, weight, weight_des, d, weight_scale, weight_zero, bias, stride, padding, input_scale, input_zero,
-                     input_qmin, input_qmax, residual, fuse_relu);
-}
-
-// (g_mu held, device guard set) d = [n_bits, sign, K, Cg, R, S]; input is 4-D
-at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des, const std::vector<int64_t>& d,
-                     const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias,
-                     const int stride, const int padding, const py::object& input_scale, const py::object& input_zero,
-                     const py::object& input_qmin, const py::object& input_qmax, const c10::optional<at::Tensor>& residual,
+                     const int stride, const int padding, const QuantArgs& qa, const c10::optional<at::Tensor>& residual,
                      const bool fuse_relu) {
     qb200_conv_shape s;
     s.N = (int32_t)input.size(0);
@@ -291,7 +376,7 @@ at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at
     const float* bias_p = bias.has_value() ? bias.value().data_ptr<float>() : nullptr;
     void* st = cur_stream();
 
-    const bool fused = !input_scale.is_none();
+    const bool fused = !qa.scale.none;
     TORCH_CHECK(fused || (!residual.has_value() && !fuse_relu),
                 "residual / fuse_relu need the activation quantizer parameters (the fused path)");
     if (residual.has_value()) {
@@ -307,43 +392,31 @@ at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at
                  "quantconv2d_float_input");
         return out;
     }
-    TORCH_CHECK(!input_zero.is_none() && !input_qmin.is_none() && !input_qmax.is_none(),
+    TORCH_CHECK(!qa.zero.none && !qa.qmin.none && !qa.qmax.none,
                 "input_scale, input_zero, input_qmin and input_qmax must be given together");
 
-    // prepared weights: derived once per (weight storage, version, descriptor)
-    const Key wk = key_of(weight, weight_des.data_ptr());
-    PreparedWeights* pw = g_prep_cache.find(wk, weight);
-    if (!pw) {
-        PreparedWeights fresh;
-        fresh.buffer = at::empty({(int64_t)qb200_conv_prepared_bytes(&s)}, weight.options());
-        check_rc(qb200_conv_prepare_weights(&s, weight.data_ptr<uint8_t>(), fresh.buffer.data_ptr(), st), "prepare_weights");
-        fresh.zero_is_zero = weight_zero.abs().max().item<float>() == 0.f;  // one sync per weight tensor
-        pw = g_prep_cache.insert(wk, weight, std::move(fresh));
-    }
+    auto pw = prepared_weights(s, weight, weight_des, weight_zero, st);
 
     std::vector<at::Tensor> keep;
     qb200_act_quant aq;
-    aq.scale = device_float(input_scale, input.device(), keep, "input_scale");
-    aq.zero = device_float(input_zero, input.device(), keep, "input_zero");
-    aq.qmin = device_float(input_qmin, input.device(), keep, "input_qmin");
-    aq.qmax = device_float(input_qmax, input.device(), keep, "input_qmax");
+    aq.scale = device_float(qa.scale, input.device(), keep);
+    aq.zero = device_float(qa.zero, input.device(), keep);
+    aq.qmin = device_float(qa.qmin, input.device(), keep);
+    aq.qmax = device_float(qa.qmax, input.device(), keep);
 
-    if (!pw->zero_is_zero) {
-        // asymmetric weights do not factor into an integer GEMM with a float zero point: fake-quantize the
-        // activations on the device (quantizer.py:215-218) and run the fp32 weight-only kernel
-        TORCH_CHECK(s.C == s.Cg, "asymmetric weights with groups > 1 are not supported");
-        TORCH_CHECK(!residual.has_value() && !fuse_relu, "residual / fuse_relu are not supported with asymmetric weights");
-        auto f = [&](const py::object& o) {
-            return THPVariable_Check(o.ptr()) ? THPVariable_Unpack(o.ptr()).detach().to(input.device(), at::kFloat).reshape({1})
-                                              : at::full({1}, o.cast<double>(), input.options());
-        };
-        auto sc = f(input_scale), ze = f(input_zero), lo = f(input_qmin), hi = f(input_qmax);
-        auto xq = at::maximum(at::minimum(at::round(input / sc - ze), hi), lo);
-        auto xdq = ((xq + ze) * sc).contiguous();
+    if (!pw->zero_is_zero || !activation_range_fits_u8(qa.qmin, qa.qmax)) {
+        // asymmetric weights do not factor into an integer GEMM with a float zero point, and activation ranges outside
+        // [0, 255] do not fit the unsigned byte operand: fake-quantize the activations on the device
+        // (quantizer.py:215-218, one engine kernel) and run the fp32 weight-only kernel
+        TORCH_CHECK(s.C == s.Cg, "asymmetric weights / signed activation ranges with groups > 1 are not supported");
+        auto xdq = fake_quantize_dev(input, aq, st);
         check_rc(qb200_quantconv2d_weightonly(&s, xdq.data_ptr<float>(), weight.data_ptr<uint8_t>(),
                                               weight_scale.data_ptr<float>(), weight_zero.data_ptr<float>(), (int32_t)n_ws,
                                               bias_p, out.data_ptr<float>(), st),
                  "quantconv2d_float_input");
+        // the optional tail, as the separate torch ops
+        if (residual.has_value()) out.add_(residual.value());
+        if (fuse_relu) out.relu_();
         return out;
     }
 
@@ -358,6 +431,35 @@ at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at
                                         (int32_t)n_ws, bias_p, &aq, &tail, ws.data_ptr(), out.data_ptr(), QB200_OUT_F32, st),
              "quantconv2d_float_input");
     return out;
+}
+
+at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& weight, const at::Tensor& weight_des,
+                                   const at::Tensor& weight_scale, const at::Tensor& weight_zero,
+                                   const c10::optional<at::Tensor>& bias, const int stride, const int padding,
+                                   const py::object& input_scale, const py::object& input_zero,
+                                   const py::object& input_qmin, const py::object& input_qmax,
+                                   const c10::optional<at::Tensor>& residual, const bool fuse_relu) {
+    // same checks, same messages as quantconv2d_float_input.cu:151-159
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    CHECK_INPUT(weight);
+    CHECK_INPUT(weight_des);
+    CHECK_INPUT(weight_scale);
+    CHECK_INPUT(weight_zero);
+    if (bias.has_value()) { CHECK_INPUT(bias.value()); }
+    TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
+    TORCH_CHECK(weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
+    CHECK_FLOAT(weight_scale);
+    CHECK_FLOAT(weight_zero);
+    if (bias.has_value()) { TORCH_CHECK(bias.value().dtype() == torch::kFloat32, "bias must be a float tensor"); }
+    QuantArgs qa{qparam(input_scale, "input_scale"), qparam(input_zero, "input_zero"), qparam(input_qmin, "input_qmin"),
+                 qparam(input_qmax, "input_qmax")};
+
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    auto d = host_des(weight_des);
+    TORCH_CHECK(d->size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+    return conv_core(input, weight, weight_des, *d, weight_scale, weight_zero, bias, stride, padding, qa, residual, fuse_relu);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -379,10 +481,12 @@ at::Tensor conv_core(const at::Tensor& input, const at::Tensor& weight, const at
 struct ChainLayer {
     at::Tensor weight, des, scale, zero;
     c10::optional<at::Tensor> bias;
+    int stride = 1, pad = 0;
+    QuantArgs qa;
     qb200_conv_shape s;
     int32_t P, Q;
     qb200_act_quant aq;
-    PreparedWeights* pw;
+    std::shared_ptr<PreparedWeights> pw;
     bool relu;
 };
 
@@ -394,12 +498,8 @@ py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, co
     const size_t n = layers.size();  // layers of the chain proper; an optional extra entry describes emit_next's consumer
     TORCH_CHECK(n >= 1, "quantconv2d_chain: no layers");
     const bool emit = !emit_next.is_none();
-    c10::cuda::CUDAGuard guard(input.device());
-    std::lock_guard<std::mutex> lock(g_mu);
-    void* st = cur_stream();
-    std::vector<at::Tensor> keep;
     std::vector<ChainLayer> L(n + (emit ? 1 : 0));
-    int32_t N = (int32_t)input.size(0), C = (int32_t)input.size(1), H = (int32_t)input.size(2), W = (int32_t)input.size(3);
+    // ---- Python objects -> C++ (GIL held) ----
     for (size_t i = 0; i < L.size(); ++i) {
         const py::tuple t = (i < n ? py::object(layers[i]) : emit_next).cast<py::tuple>();
         TORCH_CHECK(t.size() == 12, "quantconv2d_chain: each layer is a 12-tuple");
@@ -409,106 +509,116 @@ py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, co
         l.scale = t[2].cast<at::Tensor>();
         l.zero = t[3].cast<at::Tensor>();
         if (!t[4].is_none()) l.bias = t[4].cast<at::Tensor>();
-        CHECK_INPUT(l.weight);
-        CHECK_INPUT(l.des);
-        CHECK_INPUT(l.scale);
-        CHECK_INPUT(l.zero);
-        TORCH_CHECK(l.weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
-        CHECK_FLOAT(l.scale);
-        CHECK_FLOAT(l.zero);
-        if (l.bias.has_value()) {
-            CHECK_INPUT(l.bias.value());
-            TORCH_CHECK(l.bias.value().dtype() == torch::kFloat32, "bias must be a float tensor");
-        }
-        const std::vector<int64_t>& d = host_des(l.des);
-        TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
-        qb200_conv_shape& s = l.s;
-        s.N = N; s.C = C; s.H = H; s.W = W;
-        s.w_bits = (int32_t)d[0];
-        s.w_sign = d[1] != 0;
-        s.K = (int32_t)d[2]; s.Cg = (int32_t)d[3]; s.R = (int32_t)d[4]; s.S = (int32_t)d[5];
-        s.stride = t[5].cast<int>();
-        s.pad = t[6].cast<int>();
-        check_rc(qb200_conv_out_hw(&s, &l.P, &l.Q), "quantconv2d_chain");
-        TORCH_CHECK(l.weight.numel() >= qb200_packed_bytes((int64_t)s.K * s.Cg * s.R * s.S, s.w_bits),
-                    "weight is shorter than weight_des describes");
-        const int64_t n_ws = l.scale.numel();
-        TORCH_CHECK(n_ws == 1 || n_ws == s.K, "weight_scale must have 1 or ", s.K, " elements");
-        TORCH_CHECK(l.zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
-        if (l.bias.has_value()) TORCH_CHECK(l.bias.value().numel() == s.K, "bias must have ", s.K, " elements");
-        const Key wk = key_of(l.weight, l.des.data_ptr());
-        l.pw = g_prep_cache.find(wk, l.weight);
-        if (!l.pw) {
-            PreparedWeights fresh;
-            fresh.buffer = at::empty({(int64_t)qb200_conv_prepared_bytes(&s)}, l.weight.options());
-            check_rc(qb200_conv_prepare_weights(&s, l.weight.data_ptr<uint8_t>(), fresh.buffer.data_ptr(), st), "prepare_weights");
-            fresh.zero_is_zero = l.zero.abs().max().item<float>() == 0.f;
-            l.pw = g_prep_cache.insert(wk, l.weight, std::move(fresh));
-        }
-        TORCH_CHECK(l.pw->zero_is_zero, "quantconv2d_chain needs symmetric weights (weight_zero == 0)");
-        l.aq.scale = device_float(t[7], input.device(), keep, "input_scale");
-        l.aq.zero = device_float(t[8], input.device(), keep, "input_zero");
-        l.aq.qmin = device_float(t[9], input.device(), keep, "input_qmin");
-        l.aq.qmax = device_float(t[10], input.device(), keep, "input_qmax");
+        l.stride = t[5].cast<int>();
+        l.pad = t[6].cast<int>();
+        l.qa = QuantArgs{qparam(t[7], "input_scale"), qparam(t[8], "input_zero"), qparam(t[9], "input_qmin"), qparam(t[10], "input_qmax")};
+        TORCH_CHECK(!l.qa.scale.none && !l.qa.zero.none && !l.qa.qmin.none && !l.qa.qmax.none,
+                    "quantconv2d_chain: every layer needs its activation quantizer parameters");
         l.relu = t[11].cast<bool>();
-        C = s.K; H = l.P; W = l.Q;
-    }
-    if (residual.has_value()) {
-        const at::Tensor& r = residual.value();
-        CHECK_INPUT(r);
-        const ChainLayer& e = L[n - 1];
-        TORCH_CHECK(r.dtype() == torch::kFloat32 && r.dim() == 4 && r.size(0) == N && r.size(1) == e.s.K && r.size(2) == e.P &&
-                        r.size(3) == e.Q, "residual must be a float tensor shaped like the output");
-    }
-    at::Tensor x = input;          // fp32 input of the current layer (when not handed off)
-    at::Tensor ws_in;              // quantized workspace of the current layer (when handed off)
-    bool handed = false;
-    if (input_handoff.has_value()) {
-        // the first layer's input arrives already quantized (written by an earlier chain's emit_next for this very layer)
-        const at::Tensor& h = input_handoff.value();
-        CHECK_INPUT(h);
-        TORCH_CHECK(h.dtype() == torch::kByte && (size_t)h.numel() >= qb200_conv_workspace_bytes(&L[0].s),
-                    "input_handoff is not a workspace of the first layer");
-        ws_in = h;
-        handed = true;
     }
     at::Tensor out, ws_emit;
-    for (size_t i = 0; i < n; ++i) {
-        ChainLayer& l = L[i];
-        const bool last = i + 1 == n;
-        const float* bias_p = l.bias.has_value() ? l.bias.value().data_ptr<float>() : nullptr;
-        qb200_conv_tail tail;
-        tail.residual = (last && residual.has_value()) ? residual.value().data_ptr<float>() : nullptr;
-        tail.relu = l.relu ? 1 : 0;
-        tail.next_shape = nullptr;
-        tail.next_quant = nullptr;
-        tail.next_workspace = nullptr;
-        at::Tensor ws_next;
-        // the last layer hands over only on request (emit_next) and then writes BOTH the fp32 result and the bytes
-        const bool hand = (!last || emit) && qb200_conv_handoff_supported(&l.s, &L[i + 1].s) != 0;
-        if (hand) {
-            ws_next = at::empty({(int64_t)qb200_conv_workspace_bytes(&L[i + 1].s)}, l.weight.options());
-            tail.next_shape = &L[i + 1].s;
-            tail.next_quant = &L[i + 1].aq;
-            tail.next_workspace = ws_next.data_ptr();
+    {
+        py::gil_scoped_release nogil;
+        c10::cuda::CUDAGuard guard(input.device());
+        void* st = cur_stream();
+        std::vector<at::Tensor> keep;
+        int32_t N = (int32_t)input.size(0), C = (int32_t)input.size(1), H = (int32_t)input.size(2), W = (int32_t)input.size(3);
+        for (size_t i = 0; i < L.size(); ++i) {
+            ChainLayer& l = L[i];
+            CHECK_INPUT(l.weight);
+            CHECK_INPUT(l.des);
+            CHECK_INPUT(l.scale);
+            CHECK_INPUT(l.zero);
+            TORCH_CHECK(l.weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
+            CHECK_FLOAT(l.scale);
+            CHECK_FLOAT(l.zero);
+            if (l.bias.has_value()) {
+                CHECK_INPUT(l.bias.value());
+                TORCH_CHECK(l.bias.value().dtype() == torch::kFloat32, "bias must be a float tensor");
+            }
+            auto dp = host_des(l.des);
+            const std::vector<int64_t>& d = *dp;
+            TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+            qb200_conv_shape& s = l.s;
+            s.N = N; s.C = C; s.H = H; s.W = W;
+            s.w_bits = (int32_t)d[0];
+            s.w_sign = d[1] != 0;
+            s.K = (int32_t)d[2]; s.Cg = (int32_t)d[3]; s.R = (int32_t)d[4]; s.S = (int32_t)d[5];
+            s.stride = l.stride;
+            s.pad = l.pad;
+            check_rc(qb200_conv_out_hw(&s, &l.P, &l.Q), "quantconv2d_chain");
+            TORCH_CHECK(l.weight.numel() >= qb200_packed_bytes((int64_t)s.K * s.Cg * s.R * s.S, s.w_bits),
+                        "weight is shorter than weight_des describes");
+            const int64_t n_ws = l.scale.numel();
+            TORCH_CHECK(n_ws == 1 || n_ws == s.K, "weight_scale must have 1 or ", s.K, " elements");
+            TORCH_CHECK(l.zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
+            if (l.bias.has_value()) TORCH_CHECK(l.bias.value().numel() == s.K, "bias must have ", s.K, " elements");
+            l.pw = prepared_weights(s, l.weight, l.des, l.zero, st);
+            TORCH_CHECK(l.pw->zero_is_zero, "quantconv2d_chain needs symmetric weights (weight_zero == 0)");
+            TORCH_CHECK(activation_range_fits_u8(l.qa.qmin, l.qa.qmax),
+                        "quantconv2d_chain needs activation ranges inside [0, 255] (unsigned byte hand-off)");
+            l.aq.scale = device_float(l.qa.scale, input.device(), keep);
+            l.aq.zero = device_float(l.qa.zero, input.device(), keep);
+            l.aq.qmin = device_float(l.qa.qmin, input.device(), keep);
+            l.aq.qmax = device_float(l.qa.qmax, input.device(), keep);
+            C = s.K; H = l.P; W = l.Q;
         }
-        if (!hand || last) out = at::empty({l.s.N, l.s.K, l.P, l.Q}, input.options());
-        void* out_p = (hand && !last) ? nullptr : out.data_ptr();
-        if (last && hand) ws_emit = ws_next;
-        if (handed) {
-            check_rc(qb200_conv_from_workspace_ex(&l.s, ws_in.data_ptr(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
-                                                  (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, out_p, QB200_OUT_F32, st),
-                     "quantconv2d_chain");
-        } else {
-            auto ws = at::empty({(int64_t)qb200_conv_workspace_bytes(&l.s)}, l.weight.options());
-            check_rc(qb200_quantconv2d_fused_ex(&l.s, x.data_ptr<float>(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
-                                                (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, ws.data_ptr(), out_p,
-                                                QB200_OUT_F32, st),
-                     "quantconv2d_chain");
+        if (residual.has_value()) {
+            const at::Tensor& r = residual.value();
+            CHECK_INPUT(r);
+            const ChainLayer& e = L[n - 1];
+            TORCH_CHECK(r.dtype() == torch::kFloat32 && r.dim() == 4 && r.size(0) == N && r.size(1) == e.s.K && r.size(2) == e.P &&
+                            r.size(3) == e.Q, "residual must be a float tensor shaped like the output");
         }
-        handed = hand;
-        if (hand) ws_in = ws_next;
-        else x = out;
+        at::Tensor x = input;          // fp32 input of the current layer (when not handed off)
+        at::Tensor ws_in;              // quantized workspace of the current layer (when handed off)
+        bool handed = false;
+        if (input_handoff.has_value()) {
+            // the first layer's input arrives already quantized (written by an earlier chain's emit_next for this very layer)
+            const at::Tensor& h = input_handoff.value();
+            CHECK_INPUT(h);
+            TORCH_CHECK(h.dtype() == torch::kByte && (size_t)h.numel() >= qb200_conv_workspace_bytes(&L[0].s),
+                        "input_handoff is not a workspace of the first layer");
+            ws_in = h;
+            handed = true;
+        }
+        for (size_t i = 0; i < n; ++i) {
+            ChainLayer& l = L[i];
+            const bool last = i + 1 == n;
+            const float* bias_p = l.bias.has_value() ? l.bias.value().data_ptr<float>() : nullptr;
+            qb200_conv_tail tail;
+            tail.residual = (last && residual.has_value()) ? residual.value().data_ptr<float>() : nullptr;
+            tail.relu = l.relu ? 1 : 0;
+            tail.next_shape = nullptr;
+            tail.next_quant = nullptr;
+            tail.next_workspace = nullptr;
+            at::Tensor ws_next;
+            // the last layer hands over only on request (emit_next) and then writes BOTH the fp32 result and the bytes
+            const bool hand = (!last || emit) && qb200_conv_handoff_supported(&l.s, &L[i + 1].s) != 0;
+            if (hand) {
+                ws_next = at::empty({(int64_t)qb200_conv_workspace_bytes(&L[i + 1].s)}, l.weight.options());
+                tail.next_shape = &L[i + 1].s;
+                tail.next_quant = &L[i + 1].aq;
+                tail.next_workspace = ws_next.data_ptr();
+            }
+            if (!hand || last) out = at::empty({l.s.N, l.s.K, l.P, l.Q}, input.options());
+            void* out_p = (hand && !last) ? nullptr : out.data_ptr();
+            if (last && hand) ws_emit = ws_next;
+            if (handed) {
+                check_rc(qb200_conv_from_workspace_ex(&l.s, ws_in.data_ptr(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
+                                                      (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, out_p, QB200_OUT_F32, st),
+                         "quantconv2d_chain");
+            } else {
+                auto ws = at::empty({(int64_t)qb200_conv_workspace_bytes(&l.s)}, l.weight.options());
+                check_rc(qb200_quantconv2d_fused_ex(&l.s, x.data_ptr<float>(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
+                                                    (int32_t)l.scale.numel(), bias_p, &l.aq, &tail, ws.data_ptr(), out_p,
+                                                    QB200_OUT_F32, st),
+                         "quantconv2d_chain");
+            }
+            handed = hand;
+            if (hand) ws_in = ws_next;
+            else x = out;
+        }
     }
     if (!emit) return py::cast(out);
     return py::make_tuple(out, ws_emit.defined() ? py::cast(ws_emit) : py::none());
@@ -519,18 +629,17 @@ at::Tensor fake_quantize(const at::Tensor& input, const py::object& scale, const
                          const py::object& qmax) {
     CHECK_INPUT(input);
     CHECK_FLOAT(input);
+    QuantArgs qa{qparam(scale, "scale"), qparam(zero, "zero"), qparam(qmin, "qmin"), qparam(qmax, "qmax")};
+    TORCH_CHECK(!qa.scale.none && !qa.zero.none && !qa.qmin.none && !qa.qmax.none, "fake_quantize: scale, zero, qmin and qmax are required");
+    py::gil_scoped_release nogil;
     c10::cuda::CUDAGuard guard(input.device());
-    std::lock_guard<std::mutex> lock(g_mu);
     std::vector<at::Tensor> keep;
     qb200_act_quant aq;
-    aq.scale = device_float(scale, input.device(), keep, "scale");
-    aq.zero = device_float(zero, input.device(), keep, "zero");
-    aq.qmin = device_float(qmin, input.device(), keep, "qmin");
-    aq.qmax = device_float(qmax, input.device(), keep, "qmax");
-    auto out = at::empty_like(input);
-    check_rc(qb200_fake_quantize_f32(input.data_ptr<float>(), input.numel(), &aq, out.data_ptr<float>(), cur_stream()),
-             "fake_quantize");
-    return out;
+    aq.scale = device_float(qa.scale, input.device(), keep);
+    aq.zero = device_float(qa.zero, input.device(), keep);
+    aq.qmin = device_float(qa.qmin, input.device(), keep);
+    aq.qmax = device_float(qa.qmax, input.device(), keep);
+    return fake_quantize_dev(input, aq, cur_stream());
 }
 
 // max_pool2d (engine helper for the packed ResNet forward; same result as torch.nn.functional.max_pool2d)
@@ -538,6 +647,7 @@ at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int paddi
     CHECK_INPUT(input);
     CHECK_FLOAT(input);
     TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
+    py::gil_scoped_release nogil;
     c10::cuda::CUDAGuard guard(input.device());
     const int H = (int)input.size(2), W = (int)input.size(3);
     TORCH_CHECK(kernel >= 1 && stride >= 1 && padding >= 0 && 2 * padding <= kernel, "max_pool2d: bad geometry");
@@ -551,19 +661,89 @@ at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int paddi
 }
 
 // ------------------------------------------------------------------------------------------------
-// off-path ops: exported so that `from quant_engine import *` binds all 8 names; no module of
-// the reference calls them today (quantconv2d.py:198-210 has the call commented out).
+// Calibration reductions (reference range/minmax.py:62-108, :44-60, :184-203).
+//   minmax(x, granularity, flag, symmetric, update_mode=0, momentum=0.0, run_min=None, run_max=None) -> (xmin, xmax)
+//     granularity 0: per tensor (0-d results); 1: per channel — weights: dim 0; activations (flag 1): dim 1
+//     update_mode 1 / 2: run_min / run_max (float tensors shaped like the result) are updated in place (MinMax / MAMinMax)
+//   kthvalue(x, k, granularity, flag, use_abs) -> values      (torch.kthvalue(...)[0] of the estimator's flattened view)
+// ------------------------------------------------------------------------------------------------
+struct RedView {
+    int64_t A, R, B;
+    std::vector<int64_t> out_shape;
+};
+RedView reduction_view(const at::Tensor& x, int granularity, int flag) {
+    RedView v;
+    TORCH_CHECK(x.numel() > 0, "cannot reduce an empty tensor");
+    if (granularity == 0) {
+        v.A = 1; v.R = 1; v.B = x.numel();
+    } else if (flag == 1) {   // activation: (N, C, ...) -> rows = C
+        TORCH_CHECK(x.dim() >= 2, "per-channel activation ranges need at least 2 dimensions");
+        v.A = x.size(0); v.R = x.size(1); v.B = x.numel() / (x.size(0) * x.size(1));
+        v.out_shape = {x.size(1)};
+    } else {                  // weight: (C, ...) -> rows = dim 0
+        TORCH_CHECK(x.dim() >= 1, "per-channel weight ranges need at least 1 dimension");
+        v.A = 1; v.R = x.size(0); v.B = x.numel() / x.size(0);
+        v.out_shape = {x.size(0)};
+    }
+    return v;
+}
+
+std::vector<at::Tensor> minmax(const at::Tensor& input, int granularity, int flag, bool symmetric, int update_mode, double momentum,
+                               const c10::optional<at::Tensor>& run_min, const c10::optional<at::Tensor>& run_max) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    const RedView v = reduction_view(input, granularity, flag);
+    auto lo = at::empty(v.out_shape, input.options()), hi = at::empty(v.out_shape, input.options());
+    float* rmin = nullptr;
+    float* rmax = nullptr;
+    if (update_mode != 0) {
+        TORCH_CHECK(run_min.has_value() && run_max.has_value(), "minmax: update_mode needs run_min / run_max");
+        for (const at::Tensor* t : {&run_min.value(), &run_max.value()}) {
+            CHECK_INPUT((*t));
+            TORCH_CHECK(t->dtype() == torch::kFloat32 && t->numel() == v.R && t->device() == input.device(),
+                        "minmax: run_min / run_max must be float tensors with one element per row on the input's device");
+        }
+        rmin = run_min.value().data_ptr<float>();
+        rmax = run_max.value().data_ptr<float>();
+    }
+    auto ws = at::empty({(int64_t)qb200_minmax_workspace_bytes(v.R)}, input.options().dtype(at::kByte));
+    // torch evaluates `momentum * x + (1 - momentum) * old` with the python scalars cast to fp32 (1 - momentum in double first)
+    check_rc(qb200_minmax_f32(input.data_ptr<float>(), v.A, v.R, v.B, symmetric ? 1 : 0, lo.data_ptr<float>(), hi.data_ptr<float>(),
+                              update_mode, (float)momentum, (float)(1.0 - momentum), rmin, rmax, ws.data_ptr(), cur_stream()),
+             "minmax");
+    return {lo, hi};
+}
+
+at::Tensor kthvalue(const at::Tensor& input, int64_t k, int granularity, int flag, bool use_abs) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    const RedView v = reduction_view(input, granularity, flag);
+    TORCH_CHECK(k >= 1 && k <= v.A * v.B, "kthvalue(): selected number k out of range for dimension");
+    auto out = at::empty(v.out_shape, input.options());
+    auto ws = at::empty({(int64_t)qb200_kthvalue_workspace_bytes(v.R)}, input.options().dtype(at::kByte));
+    check_rc(qb200_kthvalue_f32(input.data_ptr<float>(), v.A, v.R, v.B, use_abs ? 1 : 0, k, out.data_ptr<float>(), ws.data_ptr(),
+                                cur_stream()),
+             "kthvalue");
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------
+// off-path ops: exported so that `from quant_engine import *` binds all 8 names; the reference's plain
+// float `linear` / `conv2d` (linear.cu, conv2d.cu) are not quantized operators and stay outside this engine.
 // ------------------------------------------------------------------------------------------------
 [[noreturn]] void off_path(const char* name) {
     TORCH_CHECK(false, "quant_engine.", name,
-                " is outside the hot path this engine implements (tpack, tunpack, quantconv2d_float_input)");
+                " is outside the quantized-operator path this engine implements (tpack, tunpack, quantconv2d, "
+                "quantconv2d_float_input, quantlinear, quantlinear_float_input)");
     abort();
 }
 at::Tensor linear(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int) { off_path("linear"); }
-at::Tensor quantlinear(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
-                       const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&) {
-    off_path("quantlinear");
-}
+at::Tensor conv2d(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int, int, int) { off_path("conv2d"); }
+
 // quantlinear_float_input (reference quantlinear_float_input.cu:120-182, funcs.h).  The six positional
 // arguments are the reference's: weight-only fp32 semantic in the reference kernel's accumulation order.  With the
 // activation quantizer's parameters (input_scale / zero / qmin / qmax, as for the conv op) the layer runs as the 1x1 case
@@ -584,9 +764,12 @@ at::Tensor quantlinear_float_input(const at::Tensor& input, const at::Tensor& we
     CHECK_FLOAT(weight_scale);
     CHECK_FLOAT(weight_zero);
     if (bias.has_value()) { TORCH_CHECK(bias.value().dtype() == torch::kFloat32, "bias must be a float tensor"); }
+    QuantArgs qa{qparam(input_scale, "input_scale"), qparam(input_zero, "input_zero"), qparam(input_qmin, "input_qmin"),
+                 qparam(input_qmax, "input_qmax")};
+    py::gil_scoped_release nogil;
     c10::cuda::CUDAGuard guard(input.device());
-    std::lock_guard<std::mutex> lock(g_mu);
-    const std::vector<int64_t>& d = host_des(weight_des);
+    auto dp = host_des(weight_des);
+    const std::vector<int64_t>& d = *dp;
     TORCH_CHECK(d.size() >= 4, "weight_des must hold [n_bits, sign, out_features, in_features]");
     const int64_t B = input.size(0), in_f = input.size(1), out_f = d[2];
     TORCH_CHECK(d[3] == in_f, "input has ", in_f, " features, the weight expects ", d[3]);
@@ -595,7 +778,7 @@ at::Tensor quantlinear_float_input(const at::Tensor& input, const at::Tensor& we
     TORCH_CHECK(n_ws == 1 || n_ws == out_f, "weight_scale must have 1 or ", out_f, " elements");
     TORCH_CHECK(weight_zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
     if (bias.has_value()) TORCH_CHECK(bias.value().numel() == out_f, "bias must have ", out_f, " elements");
-    if (input_scale.is_none()) {
+    if (qa.scale.none) {
         auto out = at::empty({B, out_f}, input.options());
         check_rc(qb200_quantlinear_weightonly(input.data_ptr<float>(), B, (int32_t)in_f, (int32_t)out_f, weight.data_ptr<uint8_t>(),
                                               (int32_t)d[0], d[1] != 0, weight_scale.data_ptr<float>(),
@@ -606,32 +789,168 @@ at::Tensor quantlinear_float_input(const at::Tensor& input, const at::Tensor& we
         return out;
     }
     const std::vector<int64_t> d6 = {d[0], d[1], out_f, in_f, 1, 1};
-    auto out4 = conv_core(input.view({B, in_f, 1, 1}), weight, weight_des, d6, weight_scale, weight_zero, bias, 1, 0, input_scale,
-                          input_zero, input_qmin, input_qmax, c10::nullopt, false);
+    auto out4 = conv_core(input.view({B, in_f, 1, 1}), weight, weight_des, d6, weight_scale, weight_zero, bias, 1, 0, qa,
+                          c10::nullopt, false);
     return out4.view({B, out_f});
 }
-at::Tensor conv2d(const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int, int, int) { off_path("conv2d"); }
-at::Tensor quantconv2d(const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&, const at::Tensor&,
-                       const at::Tensor&, const at::Tensor&, const at::Tensor&, const c10::optional<at::Tensor>&, int, int) {
-    off_path("quantconv2d");
+
+// quantconv2d (reference quantconv2d.cu:164-264, funcs.h:113-124, dispatched by
+// quantconv2dop.py:88-91 when input and weight are both uint8 tpack streams).  Eleven positional arguments, as the
+// reference's.  input_des = [n_bits, sign, N, C, H, W]; input_scale / input_zero: one element (per tensor) or C elements
+// (per input channel), dequantized as (q - zero) * scale like the weights.
+at::Tensor quantconv2d(const at::Tensor& input, const at::Tensor& input_des, const at::Tensor& input_scale,
+                       const at::Tensor& input_zero, const at::Tensor& weight, const at::Tensor& weight_des,
+                       const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias,
+                       const int stride, const int padding) {
+    CHECK_INPUT(input);          // quantconv2d.cu:178-189
+    CHECK_INPUT(input_des);
+    CHECK_INPUT(input_scale);
+    CHECK_INPUT(input_zero);
+    CHECK_INPUT(weight);
+    CHECK_INPUT(weight_des);
+    CHECK_INPUT(weight_scale);
+    CHECK_INPUT(weight_zero);
+    if (bias.has_value()) { CHECK_INPUT(bias.value()); }
+    TORCH_CHECK(input.dtype() == torch::kByte && weight.dtype() == torch::kByte, "input and weight must be packed uint8 tensors");
+    CHECK_FLOAT(input_scale);
+    CHECK_FLOAT(input_zero);
+    CHECK_FLOAT(weight_scale);
+    CHECK_FLOAT(weight_zero);
+    if (bias.has_value()) { TORCH_CHECK(bias.value().dtype() == torch::kFloat32, "bias must be a float tensor"); }
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    auto idp = host_des(input_des);
+    auto wdp = host_des(weight_des);
+    const std::vector<int64_t>&id = *idp, &wd = *wdp;
+    TORCH_CHECK(id.size() >= 6, "input_des must hold [n_bits, sign, N, C, H, W]");
+    TORCH_CHECK(wd.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+    const int in_bits = (int)id[0], in_sign = id[1] != 0;
+    CHECK_NBITS(in_bits);
+    qb200_conv_shape s;
+    s.N = (int32_t)id[2]; s.C = (int32_t)id[3]; s.H = (int32_t)id[4]; s.W = (int32_t)id[5];
+    s.w_bits = (int32_t)wd[0];
+    s.w_sign = wd[1] != 0;
+    s.K = (int32_t)wd[2]; s.Cg = (int32_t)wd[3]; s.R = (int32_t)wd[4]; s.S = (int32_t)wd[5];
+    s.stride = stride;
+    s.pad = padding;
+    TORCH_CHECK(s.Cg == s.C, "quantconv2d: the weight has ", s.Cg, " input channels, the input ", s.C,
+                " (the reference op has no groups, quantconv2d.cu:100-124)");
+    int32_t P = 0, Q = 0;
+    check_rc(qb200_conv_out_hw(&s, &P, &Q), "quantconv2d");
+    const int64_t n_in = (int64_t)s.N * s.C * s.H * s.W;
+    TORCH_CHECK(input.numel() >= qb200_packed_bytes(n_in, in_bits), "input is shorter than input_des describes");
+    TORCH_CHECK(weight.numel() >= qb200_packed_bytes((int64_t)s.K * s.Cg * s.R * s.S, s.w_bits),
+                "weight is shorter than weight_des describes");
+    const int64_t n_is = input_scale.numel(), n_ws = weight_scale.numel();
+    TORCH_CHECK(n_is == 1 || n_is == s.C, "input_scale must have 1 or ", s.C, " elements");
+    TORCH_CHECK(input_zero.numel() == n_is, "input_zero must have as many elements as input_scale");
+    TORCH_CHECK(n_ws == 1 || n_ws == s.K, "weight_scale must have 1 or ", s.K, " elements");
+    TORCH_CHECK(weight_zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
+    if (bias.has_value()) TORCH_CHECK(bias.value().numel() == s.K, "bias must have ", s.K, " elements");
+    const float* bias_p = bias.has_value() ? bias.value().data_ptr<float>() : nullptr;
+    void* st = cur_stream();
+    auto out = at::empty({s.N, s.K, P, Q}, input_scale.options());
+    if (n_in == 0) return out;
+    auto pw = prepared_weights(s, weight, weight_des, weight_zero, st);
+    if (n_is == 1 && pw->zero_is_zero) {
+        // per-tensor input quantizer, symmetric weights: integer GEMM on the tensor cores
+        auto ws = at::empty({(int64_t)qb200_quantconv2d_packed_workspace_bytes(&s)}, input.options());
+        check_rc(qb200_quantconv2d_packed(&s, input.data_ptr<uint8_t>(), in_bits, in_sign, input_scale.data_ptr<float>(),
+                                          input_zero.data_ptr<float>(), pw->buffer.data_ptr(), weight_scale.data_ptr<float>(),
+                                          (int32_t)n_ws, bias_p, ws.data_ptr(), out.data_ptr(), QB200_OUT_F32, st),
+                 "quantconv2d");
+        return out;
+    }
+    // per-input-channel input scales / asymmetric weights: the reference's fp32 arithmetic, in its order
+    auto xf = at::empty({s.N, s.C, s.H, s.W}, input_scale.options());
+    check_rc(qb200_dequant_packed_f32(input.data_ptr<uint8_t>(), in_bits, in_sign, n_in, (int64_t)s.H * s.W, s.C,
+                                      input_scale.data_ptr<float>(), input_zero.data_ptr<float>(), (int32_t)n_is, 0,
+                                      xf.data_ptr<float>(), st),
+             "quantconv2d");
+    check_rc(qb200_quantconv2d_weightonly(&s, xf.data_ptr<float>(), weight.data_ptr<uint8_t>(), weight_scale.data_ptr<float>(),
+                                          weight_zero.data_ptr<float>(), (int32_t)n_ws, bias_p, out.data_ptr<float>(), st),
+             "quantconv2d");
+    return out;
+}
+
+// quantlinear (reference quantlinear.cu:231-297, funcs.h:37-46, dispatched by quantlinearop.py:71-74).
+// Nine positional arguments, as the reference's.  input_des = [n_bits, sign, batch, in_features]; input_scale / input_zero:
+// 0-d (expanded over the batch, quantlinear.cu:275-281) or one element per row; weight_scale / weight_zero: 0-d or one per
+// output feature.  (q + zero) convention on both operands.
+at::Tensor quantlinear(const at::Tensor& input, const at::Tensor& input_des, const at::Tensor& input_scale,
+                       const at::Tensor& input_zero, const at::Tensor& weight, const at::Tensor& weight_des,
+                       const at::Tensor& weight_scale, const at::Tensor& weight_zero, const c10::optional<at::Tensor>& bias) {
+    CHECK_INPUT(input);          // quantlinear.cu:243-250
+    CHECK_INPUT(weight);
+    CHECK_INPUT(input_des);
+    CHECK_INPUT(input_scale);
+    CHECK_INPUT(input_zero);
+    CHECK_INPUT(weight_des);
+    CHECK_INPUT(weight_scale);
+    CHECK_INPUT(weight_zero);
+    TORCH_CHECK(input.dtype() == torch::kByte && weight.dtype() == torch::kByte, "input and weight must be packed uint8 tensors");
+    CHECK_FLOAT(input_scale);
+    CHECK_FLOAT(input_zero);
+    CHECK_FLOAT(weight_scale);
+    CHECK_FLOAT(weight_zero);
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    auto idp = host_des(input_des);
+    auto wdp = host_des(weight_des);
+    const std::vector<int64_t>&id = *idp, &wd = *wdp;
+    TORCH_CHECK(id.size() >= 4, "input_des must hold [n_bits, sign, batch, in_features]");
+    TORCH_CHECK(wd.size() >= 4, "weight_des must hold [n_bits, sign, out_features, in_features]");
+    TORCH_CHECK(id[3] == wd[3], "Input and weight do not match");                       // quantlinear.cu:259
+    const int in_bits = (int)id[0], w_bits = (int)wd[0];
+    CHECK_NBITS(in_bits);
+    CHECK_NBITS(w_bits);
+    const int64_t B = id[2], in_f = id[3], out_f = wd[2];
+    at::Tensor bias_f;
+    if (bias.has_value()) {
+        CHECK_INPUT(bias.value());
+        bias_f = bias.value().to(at::kFloat);                                              // :265
+        TORCH_CHECK(bias_f.numel() == out_f, "Weight and bias do not match");             // :266
+    }
+    TORCH_CHECK(input.numel() >= qb200_packed_bytes(B * in_f, in_bits), "input is shorter than input_des describes");
+    TORCH_CHECK(weight.numel() >= qb200_packed_bytes(out_f * in_f, w_bits), "weight is shorter than weight_des describes");
+    auto expand = [](const at::Tensor& t, int64_t n, const char* name) {
+        if (t.numel() == 1 && n != 1) return t.reshape({1}).expand({n}).contiguous();     // :275-289 (0-d -> one per row)
+        TORCH_CHECK(t.numel() == n, name, " must have 1 or ", n, " elements");
+        return t;
+    };
+    const at::Tensor is = expand(input_scale, B, "input_scale"), iz = expand(input_zero, B, "input_zero");
+    const at::Tensor wsc = expand(weight_scale, out_f, "weight_scale"), wz = expand(weight_zero, out_f, "weight_zero");
+    auto out = at::empty({B, out_f}, input_scale.options());
+    check_rc(qb200_quantlinear_packed(input.data_ptr<uint8_t>(), in_bits, id[1] != 0, is.data_ptr<float>(), iz.data_ptr<float>(), B,
+                                      (int32_t)in_f, (int32_t)out_f, weight.data_ptr<uint8_t>(), w_bits, wd[1] != 0,
+                                      wsc.data_ptr<float>(), wz.data_ptr<float>(),
+                                      bias_f.defined() ? bias_f.data_ptr<float>() : nullptr, out.data_ptr<float>(), cur_stream()),
+             "quantlinear");
+    return out;
 }
 
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.doc() = "B200 (sm_100a) implementation of JingInAI/Quantize's quant_engine hot path";
-    m.def("tpack", &tpack, "Packs the given tensor into a vector of tensors.", py::arg("x"), py::arg("n_bits"), py::arg("sign"));
-    m.def("tunpack", &tunpack, "Unpacks the given vector of tensors into a tensor.", py::arg("x"), py::arg("des"));
+    m.def("tpack", &tpack, "Packs the given tensor into a vector of tensors.", py::arg("x"), py::arg("n_bits"), py::arg("sign"),
+          py::call_guard<py::gil_scoped_release>());
+    m.def("tunpack", &tunpack, "Unpacks the given vector of tensors into a tensor.", py::arg("x"), py::arg("des"),
+          py::call_guard<py::gil_scoped_release>());
     m.def("linear", &linear, "Linear function.", py::arg("input"), py::arg("weight"), py::arg("bias") = py::none(),
           py::arg("mode") = 0);
-    m.def("quantlinear", &quantlinear, "Quantized linear function.");
+    m.def("quantlinear", &quantlinear, "Quantized linear function.", py::arg("input"), py::arg("input_des"), py::arg("input_scale"),
+          py::arg("input_zero"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
+          py::arg("bias") = py::none());
     m.def("quantlinear_float_input", &quantlinear_float_input, "Quantized linear function with float input.",
           py::arg("input"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
           py::arg("bias") = py::none(), py::arg("input_scale") = py::none(), py::arg("input_zero") = py::none(),
           py::arg("input_qmin") = py::none(), py::arg("input_qmax") = py::none());
     m.def("conv2d", &conv2d, "Conv2d function.", py::arg("input"), py::arg("weight"), py::arg("bias"), py::arg("stride"),
           py::arg("padding"), py::arg("mode") = 0);
-    m.def("quantconv2d", &quantconv2d, "Quantized conv2d function.");
+    m.def("quantconv2d", &quantconv2d, "Quantized conv2d function.", py::arg("input"), py::arg("input_des"), py::arg("input_scale"),
+          py::arg("input_zero"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
+          py::arg("bias"), py::arg("stride"), py::arg("padding"));
     m.def("quantconv2d_float_input", &quantconv2d_float_input, "Quantized conv2d function with float input.",
           py::arg("input"), py::arg("weight"), py::arg("weight_des"), py::arg("weight_scale"), py::arg("weight_zero"),
           py::arg("bias"), py::arg("stride"), py::arg("padding"), py::arg("input_scale") = py::none(),
@@ -646,6 +965,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("input"), py::arg("scale"), py::arg("zero"), py::arg("qmin"), py::arg("qmax"));
     m.def("max_pool2d", &max_pool2d, "fp32 NCHW max pooling (square kernel / stride, -inf padding, floor mode).",
           py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0);
+    m.def("minmax", &minmax, "The range estimators' (xmin, xmax) in one pass, with the optional running / moving-average update.",
+          py::arg("input"), py::arg("granularity"), py::arg("flag"), py::arg("symmetric"), py::arg("update_mode") = 0,
+          py::arg("momentum") = 0.0, py::arg("run_min") = py::none(), py::arg("run_max") = py::none());
+    m.def("kthvalue", &kthvalue, "k-th smallest value (of |x| with use_abs) of the estimator's flattened view: torch.kthvalue(...)[0].",
+          py::arg("input"), py::arg("k"), py::arg("granularity"), py::arg("flag"), py::arg("use_abs") = false);
     // engine-level helpers (not part of the reference surface)
     m.def("_launch_count", []() { return (uint64_t)qb200_launch_count(); });
     m.def("_launch_count_reset", []() { qb200_launch_count_reset(); });

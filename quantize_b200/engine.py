@@ -20,6 +20,10 @@ def load():
     global _mod
     if _mod is None:
         import torch  # noqa: F401  (libtorch symbols must be loaded first, as in the reference)
+        top = sys.modules.get("quant_engine")
+        if top is not None and hasattr(top, "_abi_version"):   # already imported as the top-level module (setup.py)
+            _mod = top
+            return _mod
         if not os.path.exists(EXT_PATH) or not os.path.exists(os.path.join(HERE, "libqb200.so")):
             raise ImportError("quant_engine is not built: run `python -m quantize_b200.build` "
                               "(or __graft_entry__.build()); this engine has no fallback implementation")

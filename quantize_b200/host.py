@@ -20,11 +20,18 @@ from . import engine as _engine
 
 
 class MinMax:
-    """reference modelzoo/modules/range/minmax.py:12-145 (percentile == 0 only)."""
+    """reference modelzoo/modules/range/minmax.py:12-145.
 
-    def __init__(self, n_bits=8, symmetric=True, signed=True, granularity="layer", percentile=0.0):
-        assert percentile == 0.0, "percentile ranges are calibration-only features outside this mirror"
+    CUDA fp32 tensors are reduced by the engine (`quant_engine.minmax`: min, max / abs-max and the estimator's state
+    update in ONE pass over the tensor instead of 2-3 torch reductions plus the update kernels; percentile ranges through
+    `quant_engine.kthvalue`, an exact radix select).  Selections are exact, so the values equal torch's bit for bit;
+    other tensors (CPU, other dtypes) take the reference's torch expressions."""
+
+    use_engine = True   # class-level switch (tests compare both paths)
+
+    def __init__(self, n_bits=8, symmetric=True, signed=True, granularity="layer", percentile=0.0, **kwargs):
         self.n_bits, self.symmetric, self.signed, self.granularity = n_bits, symmetric, signed, granularity
+        self.percentile = percentile
 
     def update(self, xmin, xmax):                                   # minmax.py:44-60
         if "xmin" not in self.__dict__:
@@ -33,20 +40,73 @@ class MinMax:
             self.xmin, self.xmax = torch.min(self.xmin, xmin), torch.max(self.xmax, xmax)
         return self.xmin, self.xmax
 
-    def range(self, x: Tensor, flag: str):                          # minmax.py:62-108
+    _update_mode = 1    # engine code of this class's update rule (qb200_minmax_f32: 1 running min/max, 2 moving average)
+
+    def _engine_ok(self, x):
+        return MinMax.use_engine and x.is_cuda and x.dtype == torch.float32 and x.numel() > 0
+
+    def _gran(self):
+        if self.granularity in ("L", "Layer", "layer"):
+            return 0
+        if self.granularity in ("C", "Channel", "channel"):
+            return 1
+        raise NotImplementedError(f"Granularity {self.granularity} not implemented.")
+
+    def _range_engine(self, x: Tensor, flag: str, accumulate: bool):
+        qe, gran, fl = _engine.load(), self._gran(), 1 if flag == "activation" else 0
+        x = x.detach().contiguous()
+        if self.percentile == 0.0:
+            have = "xmin" in self.__dict__
+            if accumulate and have and self.xmin.is_cuda and self.xmin.dtype == torch.float32 and self.xmin.is_contiguous() \
+                    and self.xmax.is_contiguous():
+                mode, mom = self._update_mode, float(getattr(self, "momentum", 0.0))
+                if mode == 2 and not (0.0 <= mom <= 1.0):
+                    mode = 1                                        # minmax.py:199-201
+                xmin, xmax = qe.minmax(x, gran, fl, self.symmetric, mode, mom, self.xmin, self.xmax)
+                self.xmin, self.xmax = xmin, xmax
+                return xmin, xmax
+            xmin, xmax = qe.minmax(x, gran, fl, self.symmetric)
+        else:
+            n = x.numel() if gran == 0 else (x.numel() // x.shape[1] if fl else x.numel() // x.shape[0])
+            if not self.symmetric:                                  # minmax.py:78-80, :92-94
+                hi_k = int(n * (1 - self.percentile)) if gran == 0 else int(n * (1 + self.percentile))
+                xmin = qe.kthvalue(x, int(n * self.percentile) + 1, gran, fl, False)
+                xmax = qe.kthvalue(x, hi_k, gran, fl, False)
+            else:                                                   # :81-84, :95-98
+                xmax = qe.kthvalue(x, int(n * (1 - self.percentile)), gran, fl, True)
+                xmin = torch.zeros_like(xmax)
+        return self.update(xmin, xmax) if accumulate else (xmin, xmax)
+
+    def range(self, x: Tensor, flag: str, accumulate=True):         # minmax.py:62-108
+        if self._engine_ok(x):
+            return self._range_engine(x, flag, accumulate)
         if self.granularity in ("L", "Layer", "layer"):
             x = x.flatten(0)
-            xmin = x.min() if not self.symmetric else torch.tensor(0.0).to(x.device)
-            xmax = x.max() if not self.symmetric else x.abs().max()
+            if self.percentile == 0.0:
+                xmin = x.min() if not self.symmetric else torch.tensor(0.0).to(x.device)
+                xmax = x.max() if not self.symmetric else x.abs().max()
+            elif not self.symmetric:
+                xmin = x.kthvalue(int(x.numel() * self.percentile) + 1)[0]
+                xmax = x.kthvalue(int(x.numel() * (1 - self.percentile)))[0]
+            else:
+                xmin = torch.tensor(0.0).to(x.device)
+                xmax = x.abs().kthvalue(int(x.numel() * (1 - self.percentile)))[0]
         elif self.granularity in ("C", "Channel", "channel"):
             if flag == "activation":
                 x = x.transpose(0, 1)
             x = x.flatten(1)
-            xmin = x.min(dim=1)[0] if not self.symmetric else torch.zeros(x.shape[0]).to(x.device)
-            xmax = x.max(dim=1)[0] if not self.symmetric else x.abs().max(dim=1)[0]
+            if self.percentile == 0.0:
+                xmin = x.min(dim=1)[0] if not self.symmetric else torch.zeros(x.shape[0]).to(x.device)
+                xmax = x.max(dim=1)[0] if not self.symmetric else x.abs().max(dim=1)[0]
+            elif not self.symmetric:
+                xmin = x.kthvalue(int(x.shape[1] * self.percentile) + 1, dim=1)[0]
+                xmax = x.kthvalue(int(x.shape[1] * (1 + self.percentile)), dim=1)[0]
+            else:
+                xmin = torch.zeros(x.shape[0]).to(x.device)
+                xmax = x.abs().kthvalue(int(x.shape[1] * (1 - self.percentile)), dim=1)[0]
         else:
             raise NotImplementedError(f"Granularity {self.granularity} not implemented.")
-        return self.update(xmin, xmax)
+        return self.update(xmin, xmax) if accumulate else (xmin, xmax)
 
     def quantize(self, xmin: Tensor, xmax: Tensor):                 # minmax.py:110-145
         n_bits = self.n_bits
@@ -71,6 +131,8 @@ class MinMax:
 
 class MAMinMax(MinMax):
     """reference minmax.py:148-203: moving-average min/max."""
+
+    _update_mode = 2
 
     def __init__(self, momentum=0.1, **kw):
         super().__init__(**kw)
@@ -217,6 +279,25 @@ class QuantConv2d(nn.Conv2d):
             self._w_sym = bool((self.w_zero == 0).all().item())
         return self._w_sym
 
+    def byte_activations(self) -> bool:
+        """the int8 hand-off stores activations as unsigned bytes: the quantizer's range must lie inside [0, 255]"""
+        if not hasattr(self, "_a_u8"):
+            a = self.a_quantizer
+            self._a_u8 = bool(0 <= float(a.qmin) <= float(a.qmax) <= 255)
+        return self._a_u8
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """reference quantconv2d.py:212-235: a checkpoint that holds `w_des` is a PACKED one — pack this (fresh) module first
+        so that the packed buffers exist with the right shapes, then load.  The reference then tunpacks the weight again
+        (its packed forward is a float conv); this mirror keeps the packed byte stream, which is what the engine consumes."""
+        device = self.weight.device
+        if prefix + "w_des" in state_dict and not self.packed:
+            self.pack()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        for cached in ("_w_sym", "_a_u8"):
+            self.__dict__.pop(cached, None)
+        self.to(device)
+
     def chain_args(self):
         """this layer as an element of engine.quantconv2d_chain's `layers` (the op's arguments + relu-after flag)."""
         a = self.a_quantizer
@@ -282,6 +363,14 @@ class QuantLinear(nn.Linear):
         self.w_quantizer = None
         self.packed = True
 
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """reference quantlinear.py:170-186 (see QuantConv2d._load_from_state_dict: the packed stream is kept)."""
+        device = self.weight.device
+        if prefix + "w_des" in state_dict and not self.packed:
+            self.pack()
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        self.to(device)
+
     def forward(self, x: Tensor) -> Tensor:                         # quantlinear.py:152-163
         if not self.packed:
             return self._forward(x)
@@ -314,8 +403,9 @@ class EngineMaxPool2d(nn.Module):
 
 
 def _chainable(convs):
-    """int8 hand-off between consecutive convs needs the engine path and symmetric weights (w_zero == 0)."""
-    return all(c.packed and c.use_engine and c.symmetric_weights() for c in convs)
+    """int8 hand-off between consecutive convs needs the engine path, symmetric weights (w_zero == 0) and activation
+    ranges that fit an unsigned byte."""
+    return all(c.packed and c.use_engine and c.symmetric_weights() and c.byte_activations() for c in convs)
 
 
 def _block_convs(block):

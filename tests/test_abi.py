@@ -73,8 +73,44 @@ def test_no_cpu_fallback(engine):
     # argument errors are the reference's (tpack.cu:13)
     with pytest.raises(RuntimeError, match=r"n_bits must be in the range \(0, 8\]"):
         engine.tpack(torch.zeros(8), 0, True)
-    with pytest.raises(RuntimeError, match="outside the hot path"):
+    with pytest.raises(RuntimeError, match="outside the quantized-operator path"):
         engine.linear(torch.zeros(2, 2), torch.zeros(2, 2))
+    # the packed-activation ops check their tensors like the reference (quantconv2d.cu:178-189, quantlinear.cu:243-250)
+    u8, i32, f1 = torch.zeros(4, dtype=torch.uint8), torch.zeros(6, dtype=torch.int32), torch.ones(1)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        engine.quantconv2d(u8, i32, f1, f1, u8, i32, f1, f1, None, 1, 0)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        engine.quantlinear(u8, i32[:4], f1, f1, u8, i32[:4], f1, f1, None)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        engine.minmax(torch.zeros(4), 0, 0, False)
+
+
+def test_setup_py_yields_top_level_quant_engine(built, tmp_path):
+    """reference engine/kernels/setup.py:5-25 + README.md:37-42: after the build, `import quant_engine` works from a clean
+    interpreter (the reference's engine/__init__.py:1-5 does `from quant_engine import *` after `import torch`)."""
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
+    r = subprocess.run([sys.executable, "setup.py", "build_ext", "--inplace"], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    code = ("import torch, quant_engine, os; assert quant_engine._abi_version() >= 200; "
+            "names = ['tpack','tunpack','linear','quantlinear','quantlinear_float_input','conv2d','quantconv2d','quantconv2d_float_input']; "
+            "assert all(callable(getattr(quant_engine, n)) for n in names); print(os.path.basename(quant_engine.__file__))")
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout.strip().startswith("quant_engine.")
+    # `setup.py build` (what `install` runs first): the module lands at the top level of the build tree, beside the package
+    base = str(tmp_path / "b")
+    r = subprocess.run([sys.executable, "setup.py", "build", "--build-base", base], cwd=ROOT, env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    libdirs = [d for d in os.listdir(base) if d.startswith("lib")]
+    assert libdirs, os.listdir(base)
+    lib = os.path.join(base, libdirs[0])
+    assert any(f.startswith("quant_engine.") and f.endswith(".so") for f in os.listdir(lib)), os.listdir(lib)
+    assert os.path.exists(os.path.join(lib, "quantize_b200", "libqb200.so"))
+    env2 = dict(env, PYTHONPATH=lib)
+    r = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), env=env2, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
 
 
 def test_product_does_not_import_oracle():

@@ -132,3 +132,59 @@ def test_fused_and_chained_block_forwards_keep_the_network_function_on_cpu(name)
             fused = host.fuse_resnet_blocks(copy.deepcopy(model), **kw)
             got = fused(x)
             assert torch.equal(got, want), kw
+
+
+def test_cpu_baseline_port_equals_the_module_fake_quant_forward():
+    """oracle/fakequant.py (bench.py's CPU arm) is pinned to host.QuantConv2d._forward — itself pinned bit-for-bit to the
+    reference module above: same quantizer parameters, same fake-quantized operands, same fp32 conv."""
+    from oracle import fakequant
+    torch.manual_seed(3)
+    conv = nn.Conv2d(12, 20, 3, 1, 1, bias=True)
+    x = torch.relu(torch.randn(4, 12, 10, 10))
+    layer = host.QuantConv2d(conv, None, dict(host.DEFAULT_W, n_bits=8), dict(host.DEFAULT_A, n_bits=8))
+    with torch.no_grad():
+        layer.calibrating = True
+        layer(x)
+        layer.calibrating = False
+        layer.w_quantizer.quant(True); layer.a_quantizer.quant(True)
+        want = layer(x)
+        aq = fakequant.minmax_asym(x, 8)
+        wq = fakequant.minmax_sym_channel(conv.weight.detach(), 8)
+        assert torch.equal(aq[0].reshape(-1), layer.a_quantizer.scale.reshape(-1)) and torch.equal(aq[1].reshape(-1), layer.a_quantizer.zero.reshape(-1))
+        assert torch.equal(wq[0].reshape(-1), layer.w_quantizer.scale.reshape(-1))
+        got = torch.nn.functional.conv2d(fakequant.fake_quant(x, *aq), fakequant.fake_quant(conv.weight.detach(), *wq), conv.bias, 1, 1)
+        assert torch.equal(got, want)
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg", [dict(symmetric=False, granularity="layer", percentile=0.01),
+                                 dict(symmetric=True, granularity="layer", percentile=0.001),
+                                 dict(symmetric=True, granularity="channel", percentile=0.02),
+                                 dict(symmetric=False, granularity="channel", percentile=0.0)])
+def test_percentile_ranges_mirror_the_reference(cfg):
+    """range/minmax.py:78-84, :92-98 (kthvalue ranges), incl. the state update over two batches."""
+    refshim.load_reference(refshim.oracle_engine_module())
+    from modelzoo.modules.range.minmax import MinMax as RefMinMax
+    torch.manual_seed(1)
+    for flag in ("weight", "activation"):
+        mine, ref = host.MinMax(n_bits=8, signed=True, **cfg), RefMinMax(n_bits=8, signed=True, **cfg)
+        for i in range(2):
+            x = torch.randn(6, 10, 5, 5) * (i + 1)
+            a, b = mine(flag, x), ref(flag, x)
+            for u, v in zip(a, b):
+                assert (torch.equal(u, v) if torch.is_tensor(u) else u == v)
+
+
+def test_oracle_reductions_equal_torch():
+    import oracle
+    torch.manual_seed(2)
+    x = torch.randn(5, 7, 3, 3)
+    for gran, flag in ((0, "weight"), (1, "weight"), (1, "activation")):
+        rows = x.reshape(1, -1) if gran == 0 else (x.transpose(0, 1).flatten(1) if flag == "activation" else x.flatten(1))
+        lo, hi = oracle.minmax(x.numpy(), gran, flag, False)
+        assert np.array_equal(np.atleast_1d(lo), rows.min(dim=1)[0].numpy()) and np.array_equal(np.atleast_1d(hi), rows.max(dim=1)[0].numpy())
+        lo, hi = oracle.minmax(x.numpy(), gran, flag, True)
+        assert np.array_equal(np.atleast_1d(hi), rows.abs().max(dim=1)[0].numpy()) and not np.any(lo)
+        for k in (1, 3, rows.shape[1]):
+            assert np.array_equal(np.atleast_1d(oracle.kthvalue(x.numpy(), k, gran, flag)), rows.kthvalue(k, dim=1)[0].numpy())
+            assert np.array_equal(np.atleast_1d(oracle.kthvalue(x.numpy(), k, gran, flag, True)), rows.abs().kthvalue(k, dim=1)[0].numpy())
