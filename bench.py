@@ -7,11 +7,16 @@
 A step = one pass of the hot path over one batch: the 53 convolutions of ResNet-50 at batch 256, every layer through
 qb200_conv_quantize_input + qb200_conv_from_workspace (the two kernels of quant_engine.quantconv2d_float_input's fused
 path) on its own synthetic fp32 NCHW input that is resident in HBM when the timed region starts.
-  value      images/s over all ranks, device-timed (CUDA events, max over ranks)
+  value      images/s over all ranks, device-timed (two CUDA events around exactly K steps, max over ranks)
   e2e        the same metric through the public API a user calls — the packed ResNet-50 built from host.QuantConv2d
              layers, whose convs call quant_engine.quantconv2d_float_input — from PINNED HOST images to HOST logits,
              host<->device copies inside the timed region
-  roofline   the dominant kernel (conv_umma_kernel): algorithmic bytes per launch / measured duration vs measured HBM peak
+  roofline   the op (activation-quantize + conv kernels): SURVEY 8(d) contract bytes per op / measured op duration vs the
+             measured HBM peak; per-kernel durations come from K more steps instrumented with per-layer CUDA events
+             (events between launches cost a few percent, so they stay out of the `value` loop)
+  strong     BASELINE config 3 as written: a GLOBAL batch of 256 split over the ranks (256 / N images per GPU), with a
+             cross-rank checksum of int32 accumulators (quantize_b200/dist.py) that verifies what the ranks computed
+  packing    tpack / tunpack GB/s (fp32 and int8 inputs, 4 and 8 bits, 2^27 elements) vs the measured HBM peak
   cpu_baseline  the reference's CPU fake-quant conv path (oracle/fakequant.py port) on a bounded sample, rank 0, N=1
 """
 import argparse
@@ -48,6 +53,9 @@ def parse_args():
     ap.add_argument("--w-bits", type=int, default=8, help="weight bits (BASELINE headline: 8)")
     ap.add_argument("--a-bits", type=int, default=8, help="activation bits (BASELINE headline: 8)")
     ap.add_argument("--sweep-out", default="", help="write the per-unique-shape layer sweep (SURVEY 8d config 5) as markdown")
+    ap.add_argument("--graph", action="store_true", help="replay one CUDA-graph capture of the step instead of launching it")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (global batch 256 / N per GPU)")
+    ap.add_argument("--no-packing", action="store_true", help="skip the tensor_packing GB/s record")
     a = ap.parse_args()
     global W_BITS, A_BITS
     W_BITS, A_BITS = a.w_bits, a.a_bits
@@ -229,30 +237,34 @@ class ConvStack:
         torch.cuda.synchronize()
 
     def step(self, stream, events=None):
-        """one pass of the hot path; events: optional per-layer (conv start, conv end, layer start) CUDA events.
-        1x1/stride-1 layers run as ONE kernel (quantizer fused into the conv's producer warps): for them the whole call
-        is the conv kernel; the other layers run the quantizer kernel and the conv kernel."""
+        """one pass of the hot path.  Without `events` every layer is ONE call of the fused op's C-ABI entry point
+        (qb200_quantconv2d_fused: what quant_engine.quantconv2d_float_input runs).  With `events` (per-layer: conv start,
+        conv end, layer start) the two kernels of a two-kernel layer are launched through qb200_conv_quantize_input +
+        qb200_conv_from_workspace — the same kernels — so that each can be timed; 1x1/stride-1 layers whose quantizer runs
+        inside the conv kernel are one launch either way."""
         L, capi = self.L, self.capi
         for i, l in enumerate(self.layers):
             s = l["spec"]
-            if events is not None:
-                events[i][2].record()
-            if l["single"]:
-                if events is not None:
-                    events[i][0].record()
+            if events is None:
                 capi.check(L.qb200_quantconv2d_fused(ctypes.byref(l["shape"]), l["x"].data_ptr(), l["prepared"].data_ptr(),
                                                      l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
                                                      ctypes.byref(l["aq"]), self.ws.data_ptr(), self.out.data_ptr(),
                                                      capi.OUT_F32, stream), "quantconv2d_fused")
             else:
-                capi.check(L.qb200_conv_quantize_input(ctypes.byref(l["shape"]), l["x"].data_ptr(), ctypes.byref(l["aq"]),
-                                                       self.ws.data_ptr(), stream), "quantize_input")
-                if events is not None:
+                events[i][2].record()
+                if l["single"]:
                     events[i][0].record()
-                capi.check(L.qb200_conv_from_workspace(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
-                                                       l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
-                                                       ctypes.byref(l["aq"]), self.out.data_ptr(), capi.OUT_F32, stream), "conv")
-            if events is not None:
+                    capi.check(L.qb200_quantconv2d_fused(ctypes.byref(l["shape"]), l["x"].data_ptr(), l["prepared"].data_ptr(),
+                                                         l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
+                                                         ctypes.byref(l["aq"]), self.ws.data_ptr(), self.out.data_ptr(),
+                                                         capi.OUT_F32, stream), "quantconv2d_fused")
+                else:
+                    capi.check(L.qb200_conv_quantize_input(ctypes.byref(l["shape"]), l["x"].data_ptr(), ctypes.byref(l["aq"]),
+                                                           self.ws.data_ptr(), stream), "quantize_input")
+                    events[i][0].record()
+                    capi.check(L.qb200_conv_from_workspace(ctypes.byref(l["shape"]), self.ws.data_ptr(), l["prepared"].data_ptr(),
+                                                           l["w_scale"].data_ptr(), s["K"], l["bias"].data_ptr(),
+                                                           ctypes.byref(l["aq"]), self.out.data_ptr(), capi.OUT_F32, stream), "conv")
                 events[i][1].record()
             if os.environ.get("QB200_BENCH_SYNC"):      # debugging aid: localise a failing launch
                 try:
@@ -262,24 +274,118 @@ class ConvStack:
                           file=sys.stderr, flush=True)
                     raise
 
+    def acc_checksum(self, layer_ids, lo, hi, stream):
+        """int64 sum of the int32 accumulators (QB200_OUT_ACC) of images [lo, hi) of the given layers: a batch-shard
+        invariant (integer sums are exact and order-free), used for the cross-rank verification."""
+        torch, L, capi = self.torch, self.L, self.capi
+        sums = []
+        for i in layer_ids:
+            l = self.layers[i]
+            s = dict(l["spec"])
+            n = hi - lo
+            cg = s["C"] // s["groups"]
+            shape = capi.conv_shape(n, s["C"], s["H"], s["W"], s["K"], cg, s["R"], s["R"], s["stride"], s["pad"], W_BITS, 1)
+            P, Q = capi.conv_out_hw(shape)
+            acc = torch.empty(n * s["K"] * P * Q, dtype=torch.int32, device=l["x"].device)
+            x = l["x"][lo:hi].contiguous()
+            capi.check(L.qb200_quantconv2d_fused(ctypes.byref(shape), x.data_ptr(), l["prepared"].data_ptr(), l["w_scale"].data_ptr(),
+                                                 s["K"], l["bias"].data_ptr(), ctypes.byref(l["aq"]), self.ws.data_ptr(),
+                                                 acc.data_ptr(), capi.OUT_ACC, stream), "quantconv2d_fused(acc)")
+            sums.append(acc.sum(dtype=torch.int64))
+        return torch.stack(sums)
+
+
+def time_stack(torch, stack, stream, K, warmup, barrier, use_graph=False):
+    """W untimed steps, then exactly K steps between two CUDA events (barrier + synchronize on both sides).
+    Returns (ms for the K steps, engine launches inside the timed region)."""
+    L = stack.L
+    for _ in range(max(warmup, 1)):
+        stack.step(stream)
+    graph = None
+    if use_graph:
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.graph(graph, stream=cap):
+            stack.step(ctypes.c_void_p(cap.cuda_stream))
+        torch.cuda.current_stream().wait_stream(cap)
+        for _ in range(2):
+            graph.replay()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    L.qb200_launch_count_reset()
+    t0.record()
+    if graph is not None:
+        for _ in range(K):
+            graph.replay()
+    else:
+        for _ in range(K):
+            stack.step(stream)
+    t1.record()
+    barrier()
+    launches = int(L.qb200_launch_count())
+    if graph is not None:       # replays launch the captured kernels without passing through the library's counter
+        L.qb200_launch_count_reset()
+        stack.step(stream)
+        torch.cuda.synchronize()
+        launches = int(L.qb200_launch_count()) * K
+    return t0.elapsed_time(t1), launches
+
+
+def packing_record(torch, capi, hbm_peak):
+    """tensor_packing GB/s (north-star item b): 2^27 signed values as fp32 (what QuantConv2d.pack hands to tpack) and as
+    int8, 4 and 8 bits; algorithmic bytes sizeof(in) + n/8 (pack), n/8 + 1 (unpack); inputs >> L2."""
+    L = capi.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n = 1 << 27
+    g = torch.Generator(device="cuda").manual_seed(0)
+    rec = {"n": n, "peak_gbs": hbm_peak}
+
+    def timed(fn, iters=10):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+
+    for dt_name, dt, code, size in (("f32", torch.float32, capi.F32, 4), ("i8", torch.int8, capi.I8, 1)):
+        for nb in (4, 8):
+            x = torch.randint(-(1 << (nb - 1)), 1 << (nb - 1), (n,), generator=g, device="cuda", dtype=torch.int32).to(dt)
+            packed = torch.empty(int(L.qb200_packed_bytes(n, nb)), dtype=torch.uint8, device="cuda")
+            flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+            out = torch.empty(n, dtype=torch.int8, device="cuda")
+            tp = timed(lambda: capi.check(L.qb200_tpack(x.data_ptr(), code, n, nb, 1, packed.data_ptr(), flag.data_ptr(), st), "tpack"))
+            tu = timed(lambda: capi.check(L.qb200_tunpack(packed.data_ptr(), n, nb, 1, out.data_ptr(), st), "tunpack"))
+            ok = bool(torch.equal(out.to(dt), x)) and int(flag.item()) == 0     # round trip at full size
+            rec[f"pack_{dt_name}_w{nb}"] = {"gbs": round(n * (size + nb / 8) / tp / 1e9, 1),
+                                            "frac": round(n * (size + nb / 8) / tp / 1e9 / hbm_peak, 3)}
+            rec[f"unpack_{dt_name}_w{nb}"] = {"gbs": round(n * (nb / 8 + 1) / tu / 1e9, 1),
+                                              "frac": round(n * (nb / 8 + 1) / tu / 1e9 / hbm_peak, 3), "round_trip_ok": ok}
+            del x, packed, out
+    return rec
+
 
 def run_b200(args):
     import torch
-    import torch.distributed as dist
     from quantize_b200 import capi, models
+    from quantize_b200 import dist as qdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+    rank, world = qdist.init_from_env("nccl")
     if args.gpus != world and rank == 0 and world > 1:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
     n_gpus = world
+    barrier = qdist.barrier
 
     specs = models.conv_layer_specs(args.model, args.batch)
     if args.layers:
@@ -289,32 +395,26 @@ def run_b200(args):
     if os.environ.get("QB200_BENCH_ALGO"):               # A/B aid: 3 = plain two-kernel tensor-core path everywhere
         L.qb200_set_conv_algo(int(os.environ["QB200_BENCH_ALGO"]))
     stack = ConvStack(specs, device, seed=rank)
-    stream_obj = torch.cuda.current_stream()
-    stream = ctypes.c_void_p(stream_obj.cuda_stream)
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    K = args.steps
+    nl = len(stack.layers)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident hot path -------------------------------------------------------------------
+    # ---- device-resident hot path: `value` ------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     sampler.start()          # nvidia-smi needs ~0.1-0.3 s to deliver its first line: start it before the warm-up
     for _ in range(max(args.warmup, 1)):
         stack.step(stream)
-    K = args.steps
-    nl = len(stack.layers)
-    events = [[tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(nl)] for _ in range(K)]
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    torch.cuda.synchronize()
     t_load = time.time()     # only samples taken from here on (GPU under the benchmark's load) are reported
-    L.qb200_launch_count_reset()
-    t0.record()
+    ms, launches = time_stack(torch, stack, stream, K, 0 if not args.graph else 1, barrier, use_graph=args.graph)
+    # ---- K more steps with per-layer events: the split into quantizer / conv kernel time -----------------
+    events = [[tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in range(nl)] for _ in range(K)]
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    i0.record()
     for k in range(K):
         stack.step(stream, events[k])
-    t1.record()
-    barrier()
-    launches = int(L.qb200_launch_count())
+    i1.record()
+    torch.cuda.synchronize()
     # the timed region lasts tens of milliseconds; if the sampler caught fewer than 2 lines inside it, keep the same
     # load running (untimed) until it has, so that the reported clocks are clocks under this load
     extra = 0
@@ -324,41 +424,59 @@ def run_b200(args):
         extra += 1
     clocks = sampler.stop(t_load)
     clocks["extra_untimed_steps_for_sampling"] = extra
-    ms = t0.elapsed_time(t1)
+    instr_ms_per_step = i0.elapsed_time(i1) / K
     conv_ms = [sum(events[k][i][0].elapsed_time(events[k][i][1]) for k in range(K)) / K for i in range(nl)]
     quant_ms = [sum(events[k][i][2].elapsed_time(events[k][i][0]) for k in range(K)) / K for i in range(nl)]
+    ms = qdist.max_over_ranks(ms, device)
     if world > 1:
-        t = torch.tensor([ms], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
         lc = torch.tensor([launches], device=device, dtype=torch.int64)
-        dist.all_reduce(lc)
+        torch.distributed.all_reduce(lc)
         launches = int(lc.item())
     ms_per_step = ms / K
     value = args.batch * n_gpus / (ms_per_step / 1e3)
 
-    # ---- roofline of the dominant kernel (conv_umma_kernel), rank 0 ------------------------------------
+    # ---- roofline (rank 0's kernels) ----------------------------------------------------------------------
+    # The unit is the OP = activation-quantize + conv kernels of one layer; its algorithmic bytes are SURVEY 8(d)'s op
+    # contract (fp32 NCHW in + fp32 NCHW out + packed weights + 12 B per output channel): 22.32 GB per ResNet-50 step.
     hbm_peak, peak_kind, peaks = measured_peaks()
     conv_total_ms = sum(conv_ms)
+    op_total_ms = conv_total_ms + sum(q for q, l in zip(quant_ms, stack.layers) if not l["single"])
     conv_bytes = sum(l["conv_bytes"] for l in stack.layers)
     total_ops = sum(l["ops"] for l in stack.layers)
     contract_bytes = models.conv_stack_work(specs, W_BITS)[1]
-    achieved = conv_bytes / nl / (conv_total_ms / nl * 1e-3) / 1e9
-    traffic = None
+    achieved = contract_bytes / (op_total_ms * 1e-3) / 1e9
+    kernel_achieved = conv_bytes / (conv_total_ms * 1e-3) / 1e9
+    traffic = kernel_dram_frac = None
     tp = os.path.join(ROOT, "profiles", "conv_umma_traffic.json")
-    if os.path.exists(tp) and not args.layers and args.batch == PER_GPU_BATCH:
+    if os.path.exists(tp) and not args.layers and args.batch == PER_GPU_BATCH and args.model == MODEL:
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "kernel": "conv_umma_kernel", "achieved": round(achieved, 1), "peak": hbm_peak,
-                "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_kind,
-                "bytes_per_launch": round(conv_bytes / nl), "us_per_launch": round(conv_total_ms / nl * 1e3, 2),
-                "launches_per_step": nl,
-                "conv_share_of_step": round(conv_total_ms / ms_per_step, 4),
-                "act_quantize_share_of_step": round(sum(quant_ms) / ms_per_step, 4),
-                "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (max(sum(q for q, l in zip(quant_ms, stack.layers) if not l["single"]), 1e-9) * 1e-3) / 1e9, 1),
+            tj = json.load(f)
+        traffic = tj.get("op_dram_bytes_per_op", tj.get("dram_bytes_per_launch"))
+        if tj.get("dram_bytes_per_launch"):
+            kernel_dram_frac = round(tj["dram_bytes_per_launch"] / (conv_total_ms / nl * 1e-3) / 1e9 / hbm_peak, 4)
+    int8_peak = None
+    ip = os.path.join(ROOT, "profiles", "int8_peak.json")
+    if os.path.exists(ip):
+        with open(ip) as f:
+            int8_peak = json.load(f).get("tops")
+    step_tops = total_ops / (ms_per_step * 1e-3) / 1e12
+    roofline = {"bound": "hbm", "kernel": "act_quantize_* + conv_umma_kernel (the op)", "achieved": round(achieved, 1),
+                "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": traffic,
+                "peak_source": peak_kind,
+                "bytes_per_op": round(contract_bytes / nl), "us_per_op": round(op_total_ms / nl * 1e3, 2), "ops_per_step": nl,
+                "how": "contract bytes (SURVEY 8d) / (quantizer + conv kernel time), CUDA events around every kernel of K instrumented steps",
+                "kernel_frac": round(kernel_achieved / hbm_peak, 4), "kernel_achieved_gbs": round(kernel_achieved, 1),
+                "kernel_dram_frac": kernel_dram_frac,
+                "kernel_note": "conv_umma_kernel alone on its own bytes (u8 NHWC or fp32 in + weights + fp32 out); kernel_dram_frac = ncu DRAM bytes of the same launches / their time",
+                "conv_share_of_step": round(conv_total_ms / instr_ms_per_step, 4),
+                "act_quantize_share_of_step": round((op_total_ms - conv_total_ms) / instr_ms_per_step, 4),
+                "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (max(op_total_ms - conv_total_ms, 1e-9) * 1e-3) / 1e9, 1),
                 "single_kernel_layers": sum(1 for l in stack.layers if l["single"]),
-                "tensor_tops": round(total_ops / (conv_total_ms * 1e-3) / 1e12, 1),
-                "tensor_frac_of_int8_spec": round(total_ops / (conv_total_ms * 1e-3) / 1e12 / INT8_PEAK_TOPS, 4),
+                "instrumented_ms_per_step": round(instr_ms_per_step, 4),
+                "tensor_tops": round(step_tops, 1),
+                "tensor_frac_of_int8_spec": round(step_tops / INT8_PEAK_TOPS, 4),
+                "tensor_frac_of_int8_measured": round(step_tops / int8_peak, 4) if int8_peak else None,
+                "int8_peak_measured_tops": int8_peak,
                 "step_contract_gbs": round(contract_bytes / (ms_per_step * 1e-3) / 1e9, 1),
                 "step_contract_frac": round(contract_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak, 4)}
     if args.per_layer and rank == 0:
@@ -399,67 +517,138 @@ def run_b200(args):
                         f"{100 * ops / t_us / 1e6 / INT8_PEAK_TOPS:.1f} | {'hbm' if t_hbm >= t_tc else 'tensor'} | {bound / t_us:.2f} |\n")
             f.write(f"\nwhole stack: {tot_t:.0f} us measured, {tot_b:.0f} us at the per-layer bounds = {tot_b / tot_t:.2f}\n")
 
+    # ---- strong scaling: BASELINE config 3 as written — a global batch of 256, 256 / N images per GPU ------------
+    strong = None
+    headline = (args.model, args.batch) == (MODEL, PER_GPU_BATCH) and not args.layers
+    del stack
+    torch.cuda.empty_cache()
+    sstack = None
+    if headline and not args.no_strong:
+        lo, hi = qdist.shard_range(PER_GPU_BATCH, rank, world)
+        if world == 1:
+            s_ms_per_step, verify = ms_per_step, None
+        else:
+            # every rank builds the SAME global batch (seed 0) and keeps its slice: rows [r*256/N, (r+1)*256/N)
+            gspecs = models.conv_layer_specs(args.model, PER_GPU_BATCH)
+            gstack = ConvStack(gspecs, device, seed=0)
+            vlayers = [0, 2, 13, 29, 48]                     # stem, 3x3 @56, 1x1 @28, 3x3 @14, 3x3 @7
+            mine = gstack.acc_checksum(vlayers, lo, hi, stream)
+            nlo, nhi = qdist.shard_range(PER_GPU_BATCH, (rank + 1) % world, world)
+            neighbour = gstack.acc_checksum(vlayers, nlo, nhi, stream)   # this rank recomputes its neighbour's shard
+            whole = gstack.acc_checksum(vlayers, 0, PER_GPU_BATCH, stream) if rank == 0 else None
+            gathered = qdist.gather_batch(mine.reshape(1, -1), world)    # [world, layers] int64, via NCCL
+            ok = bool(torch.equal(gathered[(rank + 1) % world], neighbour))
+            if rank == 0:
+                ok = ok and bool(torch.equal(gathered.sum(0), whole))    # shard sums add up to the unsharded batch
+            okt = torch.tensor([1 if ok else 0], device=device)
+            torch.distributed.all_reduce(okt, op=torch.distributed.ReduceOp.MIN)
+            verify = {"cross_rank_checksum_ok": bool(okt.item()), "layers": vlayers,
+                      "what": "int64 sums of int32 accumulators per shard: all-gathered (NCCL), each rank recomputes its "
+                              "neighbour's shard, rank 0 checks that the shard sums add up to the unsharded batch",
+                      "checksums_rank0_view": [int(v) for v in gathered.sum(0).tolist()]}
+            del gstack, mine, neighbour, whole
+            torch.cuda.empty_cache()
+            sspecs = models.conv_layer_specs(args.model, hi - lo)
+            sstack = ConvStack(sspecs, device, seed=rank)
+            s_ms, _ = time_stack(torch, sstack, stream, K, max(args.warmup, 1), barrier, use_graph=args.graph)
+            s_ms_per_step = qdist.max_over_ranks(s_ms, device) / K
+            del sstack
+            torch.cuda.empty_cache()
+        s_value = PER_GPU_BATCH / (s_ms_per_step / 1e3)
+        strong = {"global_batch": PER_GPU_BATCH, "per_gpu_batch": hi - lo, "img_s": round(s_value, 1),
+                  "ms_per_step": round(s_ms_per_step, 4),
+                  # one GPU's rate on the full batch is what each rank of the weak run achieves: 256 / ms_per_step
+                  "efficiency_vs_n1": round((s_value / n_gpus) / (PER_GPU_BATCH / (ms_per_step / 1e3)), 4),
+                  "verify": verify}
+
     # ---- end to end through the public op API: host images -> logits on host ----------------------------
     e2e = None
     if not args.no_e2e and not args.layers:
-        del stack
-        torch.cuda.empty_cache()
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
         net = models.build_packed(args.model, W_BITS, A_BITS, calib_batch=8, device=device, seed=0, fuse_blocks=True,
                                   chain_blocks=not args.no_chain, cross_block=not args.no_chain)
         hw = models.INPUT_HW[args.model]
-        host_in = torch.randn(args.batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
         with torch.no_grad():
             n_classes = net(torch.zeros(1, 3, hw, hw, device=device)).shape[1]
-        host_out = torch.empty(args.batch, n_classes, dtype=torch.float32).pin_memory()
-        dev_in = [torch.empty_like(host_in, device=device) for _ in range(2)]
-        copy_stream = torch.cuda.Stream(device=device)
         compute = torch.cuda.current_stream()
-        ev_copied = [torch.cuda.Event() for _ in range(2)]
-        ev_used = [torch.cuda.Event() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=device)
 
-        def issue_copy(k):          # H2D of step k's images on the copy stream, into the buffer step k-2 has released
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ev_used[k % 2])
-                dev_in[k % 2].copy_(host_in, non_blocking=True)
-                ev_copied[k % 2].record(copy_stream)
+        def run_e2e(batch):
+            """every step: H2D of its inputs (pinned host memory), forward, D2H of its logits; the H2D of step k+1 runs on
+            a copy stream into the second device buffer while step k computes.  Returns ms per step (device events)."""
+            host_in = torch.randn(batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
+            host_out = torch.empty(batch, n_classes, dtype=torch.float32).pin_memory()
+            dev_in = [torch.empty_like(host_in, device=device) for _ in range(2)]
+            ev_copied = [torch.cuda.Event() for _ in range(2)]
+            ev_used = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_steps(n):           # every step: H2D of its inputs, forward, D2H of its logits; copies overlap compute
-            issue_copy(0)
-            for k in range(n):
-                if k + 1 < n:
-                    issue_copy(k + 1)
-                compute.wait_event(ev_copied[k % 2])
-                with torch.no_grad():
-                    logits = net(dev_in[k % 2])
-                ev_used[k % 2].record(compute)
-                host_out.copy_(logits, non_blocking=True)
+            def issue_copy(k):          # H2D of step k's images on the copy stream, into the buffer step k-2 has released
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(ev_used[k % 2])
+                    dev_in[k % 2].copy_(host_in, non_blocking=True)
+                    ev_copied[k % 2].record(copy_stream)
 
-        for ev in ev_used:
-            ev.record(compute)
-        e2e_steps(max(args.warmup, 1))
-        barrier()
-        L.qb200_launch_count_reset()
-        wall0 = time.perf_counter()
-        t0.record()
-        e2e_steps(K)
-        t1.record()
-        barrier()
-        wall = time.perf_counter() - wall0
-        e_ms = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([e_ms], device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e_ms = float(t.item())
-        e2e = {"value": round(args.batch * n_gpus / (e_ms / K / 1e3), 1), "unit": "images/s",
-               "h2d_bytes_per_step": host_in.numel() * 4, "d2h_bytes_per_step": host_out.numel() * 4,
-               "ms_per_step": round(e_ms / K, 3), "wall_ms_per_step": round(wall / K * 1e3, 3),
+            def steps(n):
+                issue_copy(0)
+                for k in range(n):
+                    if k + 1 < n:
+                        issue_copy(k + 1)
+                    compute.wait_event(ev_copied[k % 2])
+                    with torch.no_grad():
+                        logits = net(dev_in[k % 2])
+                    ev_used[k % 2].record(compute)
+                    host_out.copy_(logits, non_blocking=True)
+
+            for ev in ev_used:
+                ev.record(compute)
+            steps(max(args.warmup, 1))
+            # the H2D copy alone (same buffers, nothing else running): names the bound of the e2e number at N GPUs
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                dev_in[0].copy_(host_in, non_blocking=True)
+            c1.record()
+            barrier()
+            h2d_gbs = host_in.numel() * 4 * 3 / (c0.elapsed_time(c1) * 1e-3) / 1e9
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            L.qb200_launch_count_reset()
+            wall0 = time.perf_counter()
+            e0.record()
+            steps(K)
+            e1.record()
+            barrier()
+            wall = time.perf_counter() - wall0
+            e_ms = qdist.max_over_ranks(e0.elapsed_time(e1), device)
+            return e_ms / K, wall / K * 1e3, host_in.numel() * 4, host_out.numel() * 4, int(L.qb200_launch_count()) // K, h2d_gbs
+
+        e_ms, wall_ms, h2d, d2h, e_launches, h2d_gbs = run_e2e(args.batch)
+        e2e = {"value": round(args.batch * n_gpus / (e_ms / 1e3), 1), "unit": "images/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": round(e_ms, 3), "wall_ms_per_step": round(wall_ms, 3),
+               "h2d_gbs_per_gpu": round(h2d_gbs, 1),
+               "h2d_ms_per_step_alone": round(h2d / (h2d_gbs * 1e9) * 1e3, 3),
                "api": "models.build_packed(resnet50, fuse_blocks=True, chain_blocks=%s) forward: host.QuantConv2d -> "
                       "quant_engine.quantconv2d_float_input / quantconv2d_chain (ReLU / residual add of each block run in the "
                       "conv epilogues; with chain_blocks the activations between the convs of a block stay int8)" % (not args.no_chain),
                "pipelining": "H2D of step k+1 (copy stream, double buffer) overlaps the forward of step k; all copies inside the timed region",
-               "engine_launches_per_step": int(L.qb200_launch_count()) // K}
+               "engine_launches_per_step": e_launches}
+        if strong is not None:
+            if world == 1:
+                strong["e2e_img_s"] = e2e["value"]
+            else:
+                lo, hi = qdist.shard_range(PER_GPU_BATCH, rank, world)
+                se_ms = run_e2e(hi - lo)[0]
+                strong["e2e_img_s"] = round(PER_GPU_BATCH / (se_ms / 1e3), 1)
+                strong["e2e_ms_per_step"] = round(se_ms, 3)
+        del net
+        torch.cuda.empty_cache()
+
+    packing = None
+    if rank == 0 and n_gpus == 1 and not args.no_packing and not args.layers:
+        packing = packing_record(torch, capi, hbm_peak)
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline and not args.layers:
@@ -479,12 +668,14 @@ def run_b200(args):
                        "per_gpu_batch": args.batch, "global_batch": args.batch * n_gpus, "w_bits": W_BITS, "a_bits": A_BITS,
                        "parallelism": f"batch-sharded x{n_gpus}, weights replicated, no collective on the data path",
                        "l2": "every layer streams its own input/output: 22.3 GB per step >> 126 MB L2, no flush needed",
+                       "launch": "cuda graph replay" if args.graph else "stream launches (programmatic dependent launch)",
                        "ops_per_step": total_ops, "contract_bytes_per_step": contract_bytes},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu_baseline,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "e2e": e2e, "strong": strong,
+            "packing": packing, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        torch.distributed.destroy_process_group()
 
 
 def _only_json_on_stdout():
