@@ -216,6 +216,7 @@ class ConvStack:
             max_out = max(max_out, s["N"] * s["K"] * P * Q)
             ops = 2 * s["N"] * s["K"] * P * Q * cg * s["R"] * s["R"]
             single = bool(self.L.qb200_conv_is_single_kernel(ctypes.byref(shape), x.data_ptr()))
+            chunked = int(self.L.qb200_conv_rows_chunk(ctypes.byref(shape))) > 0   # im2col rows in L2-sized chunks of images
             # strided 1x1 layers only touch the sampled pixels; few-channel layers go through im2col rows
             sub = s["R"] == 1 and s["stride"] > 1 and s["pad"] == 0
             in_pix = s["N"] * (P * Q if sub else s["H"] * s["W"])
@@ -230,8 +231,11 @@ class ConvStack:
             else:        # quantizer kernel (fp32 in, u8 out) + conv kernel (u8 in, fp32 out)
                 conv_bytes = in_pix * Cp + w_bytes + 4 * s["N"] * s["K"] * P * Q
                 quant_bytes = 4 * s["C"] * in_pix + in_pix * Cp
+            if chunked:      # one fused call (quantizer and conv kernels alternate per chunk): its bytes are both kernels'
+                conv_bytes, quant_bytes = conv_bytes + quant_bytes, 0
             self.layers.append(dict(spec=s, x=x, shape=shape, prepared=prepared, aq=aq, aq_t=aq_t, w_scale=w_scale,
-                                    bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed, single=single))
+                                    bias=bias, ops=ops, conv_bytes=conv_bytes, quant_bytes=quant_bytes, packed=packed,
+                                    single=single or chunked, chunked=chunked))
         self.ws = torch.empty(max_ws, dtype=torch.uint8, device=device)
         self.out = torch.empty(max_out, dtype=torch.float32, device=device)
         torch.cuda.synchronize()
@@ -471,7 +475,7 @@ def run_b200(args):
                 "conv_share_of_step": round(conv_total_ms / instr_ms_per_step, 4),
                 "act_quantize_share_of_step": round((op_total_ms - conv_total_ms) / instr_ms_per_step, 4),
                 "act_quantize_gbs": round(sum(l["quant_bytes"] for l in stack.layers) / (max(op_total_ms - conv_total_ms, 1e-9) * 1e-3) / 1e9, 1),
-                "single_kernel_layers": sum(1 for l in stack.layers if l["single"]),
+                "single_kernel_layers": sum(1 for l in stack.layers if l["single"] and not l["chunked"]),
                 "instrumented_ms_per_step": round(instr_ms_per_step, 4),
                 "tensor_tops": round(step_tops, 1),
                 "tensor_frac_of_int8_spec": round(step_tops / INT8_PEAK_TOPS, 4),

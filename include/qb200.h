@@ -179,6 +179,13 @@ int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const 
                                int32_t out_kind, void* stream);
 int qb200_conv_handoff_supported(const qb200_conv_shape* s, const qb200_conv_shape* next_shape);
 
+/* Few-channel layers (the RGB stem) run through materialised im2col rows; when the rows of the whole batch exceed L2,
+ * qb200_quantconv2d_fused processes the batch in chunks of `images` images through the same workspace region so the rows
+ * stay L2-resident (same kernels, same bits).  qb200_conv_rows_chunk: the chunk this layer will use (0 = whole batch);
+ * off by default (measured slower on B200: the chunks are too small to fill the GPU); environment QB200_ROWS_CHUNK. */
+void qb200_set_rows_chunk(int images);
+int qb200_conv_rows_chunk(const qb200_conv_shape* s);
+
 /* 1 when qb200_quantconv2d_fused runs this layer as ONE kernel (the quantizer runs in the conv kernel's producer warps
  * and no workspace is written), else 0.  Supported for 1x1, stride 1, pad 0, C % 64 == 0, H*W % 4 == 0, 16-byte
  * aligned x; chosen by default where it was measured to win (C == 64, feature map >= 28x28). */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_quantlinear_weightonly", "qb200_fake_quantize_f32",
     "qb200_unpack_act_nhwc", "qb200_dequant_packed_f32", "qb200_quantconv2d_packed", "qb200_quantconv2d_packed_workspace_bytes",
     "qb200_quantlinear_packed", "qb200_minmax_f32", "qb200_minmax_workspace_bytes", "qb200_kthvalue_f32",
-    "qb200_kthvalue_workspace_bytes",
+    "qb200_kthvalue_workspace_bytes", "qb200_set_rows_chunk", "qb200_conv_rows_chunk",
 ]
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
@@ -83,6 +83,9 @@ def lib():
         L.qb200_quantconv2d_fused_ex.argtypes = [sp, vp, vp, vp, i32, vp, ap, ctypes.POINTER(ConvTail), vp, vp, i32, vp]
         L.qb200_conv2d_q8_nhwc.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, i32, vp]
         L.qb200_conv_is_single_kernel.argtypes = [sp, vp]
+        L.qb200_set_rows_chunk.argtypes = [ctypes.c_int]
+        L.qb200_set_rows_chunk.restype = None
+        L.qb200_conv_rows_chunk.argtypes = [sp]
         L.qb200_conv_quantize_input.argtypes = [sp, vp, ap, vp, vp]
         L.qb200_conv_from_workspace.argtypes = [sp, vp, vp, vp, i32, vp, ap, vp, i32, vp]
         L.qb200_quantconv2d_weightonly.argtypes = [sp, vp, vp, vp, vp, i32, vp, vp, vp]

@@ -16,6 +16,7 @@
 // quantizes in registers, writes four 16-byte channel vectors into an XOR-swizzled shared tile, and the block
 // copies the tile out as whole contiguous NHWC rows.  HBM-bound: bytes per element = 4 (read) + Cp/C (write).
 #include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "quant_math.cuh"
@@ -214,6 +215,100 @@ act_quantize_nhwc_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// band kernel: planes that the vector kernel cannot take (H*W % 4 != 0: 7x7, 9x9, ...) and sub-sampled inputs (1x1 / stride s).
+// The scalar kernel above keeps 16 four-byte loads in flight per thread and serialises one HBM round trip per 16-channel
+// chunk: 1.7 TB/s on 7x7 planes, 2.3-2.6 TB/s sub-sampled (profiles/README.md).  Here a block = (image, 32-channel slab,
+// band of the input rows that are actually read): phase 1 streams the band of every channel into shared memory with
+// cp.async (16 / 8 / 4 bytes per copy, whatever the row alignment allows) — the whole block's input is in flight at once —
+// phase 2 turns it: a thread owns one output pixel, reads its 32 channels from shared memory (lanes = consecutive pixels:
+// conflict-free), quantizes them and writes one full 32-byte sector of the NHWC row.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBandCh = 32;            // channels per block
+constexpr int kBandFloats = 384;       // floats per channel and band in shared memory (48 KB per block)
+
+__device__ __forceinline__ void cp_async_n(void* dst_smem, const void* src, int bytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+
+// rows_band input rows per band (each `sub`-th row of the image), `seg` floats per row (the whole row), vec = bytes per copy.
+// dense (sub == 1, band = whole plane, vec chosen for the CONTIGUOUS slab of channels): one long segment per block.
+__global__ void __launch_bounds__(256)
+act_quantize_band_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int C, int Cp, int H, int W, int sub, int P_out,
+                         int Q_out, int rows_band, int n_bands, int vec, const float* __restrict__ p_scale,
+                         const float* __restrict__ p_zero, const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) float band[];   // [kBandCh][plane], plane = rows_band * W floats
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int n_slabs = Cp / kBandCh;
+    int b = blockIdx.x;
+    const int bi = b % n_bands; b /= n_bands;
+    const int slab = b % n_slabs;
+    const int n = b / n_slabs;
+    const int c0 = slab * kBandCh;
+    const int nch = min(kBandCh, C - c0);            // <= 0: a slab of padded channels only (all zeros)
+    const int r0 = bi * rows_band;                   // first output row of the band
+    const int rows = min(rows_band, P_out - r0);
+    const int plane = rows_band * W;
+    const int HW = H * W;
+    // ---- phase 1: global -> shared ----
+    if (nch > 0) {
+        const float* src0 = x + ((int64_t)n * C + c0) * HW;
+        const int fpc = vec >> 2;                    // floats per copy
+        if (sub == 1 && n_bands == 1) {
+            // the slab's planes are one contiguous run of nch * HW floats (plane == HW)
+            const int total = nch * HW;
+            const int n_copies = total / fpc;
+            for (int i = threadIdx.x; i < n_copies; i += blockDim.x) cp_async_n(band + i * fpc, src0 + i * fpc, vec);
+            for (int i = n_copies * fpc + threadIdx.x; i < total; i += blockDim.x) cp_async_n(band + i, src0 + i, 4);
+        } else {
+            const int per_row = W / fpc;             // W % fpc == 0 by construction of vec
+            const int n_copies = nch * rows * per_row;
+            for (int i = threadIdx.x; i < n_copies; i += blockDim.x) {
+                const int seg = i / per_row, o = (i - seg * per_row) * fpc;
+                const int c = seg / rows, r = seg - c * rows;
+                cp_async_n(band + c * plane + r * W + o, src0 + (int64_t)c * HW + (int64_t)(r0 + r) * sub * W + o, vec);
+            }
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // ---- phase 2: one thread = one output pixel x 32 channels ----
+    const int npix = rows * Q_out;
+    for (int i = threadIdx.x; i < npix; i += blockDim.x) {
+        const int r = i / Q_out, qq = i - r * Q_out;
+        const float* s = band + r * W + qq * sub;
+        uint32_t w[8];
+        if (nch == kBandCh) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = s[j * plane];
+            quant_row<8>(v, w, p);
+        } else {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = j < nch ? s[j * plane] : 0.f;
+            quant_row<8>(v, w, p);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {                  // padded channels must be exactly 0 even when qmin > 0
+                uint32_t keep = 0;
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb)
+                    if (k * 4 + bb < nch) keep |= 0xFFu << (8 * bb);
+                w[k] &= keep;
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(q + (((int64_t)n * P_out + r0 + r) * Q_out + qq) * Cp + c0);
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // few-channel layers (RGB stem): quantize straight into im2col rows.
 // One block = 8 output rows of one image.  The input rows they touch are quantized ONCE into a shared patch of packed
 // words (one word = the <=4 channels of a pixel); pixels outside the image are 0, so that padded taps add nothing to
@@ -404,6 +499,54 @@ int launch_act_quantize_im2col(const float* x, const ConvGeom& g, int Kcol, cons
 
 }  // namespace qb200
 
+
+namespace qb200 {
+namespace {
+// Launch the band kernel for (optionally sub-sampled) fp32 NCHW -> compact u8 [N, P_out, Q_out, Cp].  Returns -100 when the
+// shape does not fit its shared-memory band (the caller then uses the scalar kernel).
+int launch_band(const float* x, uint8_t* q, int N, int C, int Cp, int H, int W, int sub, const qb200_act_quant* aq, cudaStream_t st) {
+    const int P_out = (H + sub - 1) / sub, Q_out = (W + sub - 1) / sub;
+    const int HW = H * W;
+    int rows_band, n_bands, vec;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(x);
+    if (sub == 1 && HW <= kBandFloats) {
+        rows_band = H;
+        n_bands = 1;
+        // a slab starts (n * C + 32 * k) * HW floats from x: 16-byte copies need C * HW to be a multiple of 4 floats
+        const int64_t img = (int64_t)C * HW;
+        vec = (a % 16 == 0 && img % 4 == 0) ? 16 : ((a % 8 == 0 && img % 2 == 0) ? 8 : 4);
+    } else {
+        if (W > kBandFloats) return -100;
+        rows_band = kBandFloats / W;
+        if (rows_band > P_out) rows_band = P_out;
+        n_bands = (P_out + rows_band - 1) / rows_band;
+        vec = (a % 16 == 0 && W % 4 == 0) ? 16 : ((a % 8 == 0 && W % 2 == 0) ? 8 : 4);
+    }
+    const int plane = rows_band * W;
+    const size_t smem = (size_t)kBandCh * plane * sizeof(float);
+    if (smem > 48 * 1024) return -100;
+    const int64_t blocks = (int64_t)N * (Cp / kBandCh) * n_bands;
+    if (blocks >= (1ll << 31)) return -100;
+    const int npix = rows_band * Q_out;
+    const int threads = npix >= 192 ? 256 : (npix >= 96 ? 128 : 64);
+    QB_CUDA(launch_pdl(act_quantize_band_kernel, dim3((unsigned)blocks), dim3(threads), smem, st, x, q, C, Cp, H, W, sub, P_out, Q_out,
+                       rows_band, n_bands, vec, aq->scale, aq->zero, aq->qmin, aq->qmax));
+    QB_LAUNCH_CHECK();
+    return 0;
+}
+// QB200_BAND_QUANT: 0 = never, 1 = planes the vector kernel cannot take + sub-sampled inputs, 2 = also every dense plane of
+// at most kBandFloats pixels (14x14, 7x7 ...) — A/B switch
+int band_mode() {
+    static const int mode = [] {
+        const char* e = getenv("QB200_BAND_QUANT");
+        return e ? atoi(e) : 1;
+    }();
+    return mode;
+}
+bool band_enabled() { return band_mode() != 0; }
+}  // namespace
+}  // namespace qb200
+
 extern "C" {
 
 int32_t qb200_padded_channels(int32_t C) { return (C + 31) / 32 * 32; }
@@ -428,12 +571,21 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
         const int blocks = (int)std::min<int64_t>(ceil_div64(words, 256), (int64_t)kNumSMs * 8);
         QB_CUDA(launch_pdl(act_quantize_rows_kernel, dim3(blocks), dim3(256), 0, st, x, reinterpret_cast<uint32_t*>(q_nhwc), words, C, Cp,
                            aq->scale, aq->zero, aq->qmin, aq->qmax));
+    } else if (band_mode() == 2 && HW <= kBandFloats) {
+        const int rc = launch_band(x, q_nhwc, N, C, Cp, H, W, 1, aq, st);
+        if (rc != -100) return rc;
+        QB_REQUIRE(false, QB200_EUNSUPPORTED, "act_quantize: band kernel refused a small plane");
     } else if (HW % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0)
         QB_CUDA(launch_pdl(act_quantize_nhwc_vec4_kernel, dim3(grid), dim3(kThreads), 0, st, x, q_nhwc, total, C, Cp, HW, ps, aq->scale, aq->zero, aq->qmin,
                                                                   aq->qmax));
-    else
+    else {
+        if (band_enabled()) {
+            const int rc = launch_band(x, q_nhwc, N, C, Cp, H, W, 1, aq, st);
+            if (rc != -100) return rc;
+        }
         QB_CUDA(launch_pdl(act_quantize_nhwc_kernel, dim3(grid), dim3(kThreads), 0, st, x, q_nhwc, total, C, Cp, HW, 1, W, W, HW, ps, aq->scale, aq->zero,
                                                              aq->qmin, aq->qmax));
+    }
     QB_LAUNCH_CHECK();
     return 0;
 }
@@ -447,6 +599,13 @@ int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb20
                "act_quantize: activation quantizer parameters missing");
     QB_REQUIRE(g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1, QB200_EINVAL, "act_quantize_subsampled: not a strided 1x1 layer");
     const int64_t total = (int64_t)g.N * g.P * g.Q;
+    // (pad == 0 and R == 1: P = (H - 1) / stride + 1 = ceil(H / stride), what the band kernel derives)
+    // measured (profiles/README.md, round 2): the band kernel LOSES on sub-sampled inputs (256ch @56 s2: 132 vs 116 us;
+    // 1024ch @14 s2: 58 vs 49 us — 8-byte copies of half-used rows), so it is opt-in here
+    if (band_mode() == 3) {
+        const int rc = launch_band(x, q, g.N, g.C, g.Cp, g.H, g.W, g.stride, aq, st);
+        if (rc != -100) return rc;
+    }
     dim3 grid((unsigned)ceil_div64(total, kPix), (unsigned)((g.Cp + kCw - 1) / kCw));
     QB_CUDA(launch_pdl(act_quantize_nhwc_kernel, dim3(grid), dim3(kThreads), 0, st, x, q, total, g.C, g.Cp, g.H * g.W, g.stride, g.W, g.Q, g.P * g.Q,
                                                          PadSpec{0, g.H, g.W}, aq->scale, aq->zero, aq->qmin, aq->qmax));

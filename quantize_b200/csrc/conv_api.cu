@@ -1,4 +1,5 @@
 // C-ABI entry points of the fused quantized convolution (see include/qb200.h).
+#include <stdlib.h>
 #include "common.cuh"
 #include "conv_common.cuh"
 
@@ -6,6 +7,17 @@ namespace qb200 {
 namespace {
 
 int g_conv_algo = QB200_ALGO_AUTO;
+
+// Few-channel layers (the RGB stem) go through materialised im2col rows: 192 B per output pixel, 617 MB for ResNet-50's
+// stem at batch 256 — written by the quantizer and read back by the conv, 1.2 GB of DRAM traffic the op contract does not
+// contain.  Processing the batch in chunks of a few images through the SAME workspace region keeps the rows in the
+// 126 MB L2: chunk c+1's quantizer overwrites what chunk c's conv has just read.  0 = whole batch at once (the default:
+// measured on B200 the chunked stem is SLOWER — 16 images: 1070 us, 32: 690 us, whole batch 433 us — because the row
+// writer has one block per 8 output rows and a 16-image chunk is 224 blocks on 148 SMs; kept as a switch, off).
+int g_rows_chunk = [] {
+    const char* e = getenv("QB200_ROWS_CHUNK");
+    return e ? atoi(e) : 0;
+}();
 
 int resolve_algo(const ConvGeom& g) {
     int algo = g_conv_algo;
@@ -42,6 +54,17 @@ bool handoff_ok(const qb200_conv_shape& s, const qb200_conv_shape& n) {
     if (n.N != s.N || n.C != s.K || n.H != g.P || n.W != g.Q) return false;
     if (workspace_is_im2col(gn, prepared_layout(n)) || uses_subsampled_input(gn)) return false;
     return true;
+}
+
+// images per chunk for a layer whose workspace holds im2col rows (0: run the whole batch at once)
+int rows_chunk_images(const qb200_conv_shape& s, const qb200_conv_tail* tail) {
+    if (g_rows_chunk <= 0 || s.N <= g_rows_chunk || (tail && tail->next_shape)) return 0;
+    const ConvGeom g = make_geom(s);
+    if (!workspace_is_im2col(g, prepared_layout(s))) return 0;
+    // only worth it when the rows of the whole batch do not fit L2 anyway
+    const PreparedLayout L = prepared_layout(s);
+    if ((int64_t)s.N * g.P * g.Q * L.Kcol < (64ll << 20)) return 0;
+    return g_rows_chunk;
 }
 
 int quantize_input(const qb200_conv_shape* s, const float* x, const qb200_act_quant* aq, uint8_t* ws, cudaStream_t st) {
@@ -124,6 +147,12 @@ extern "C" {
 
 int qb200_watchdog_code(void) { return qb200::watchdog_code(); }
 
+void qb200_set_rows_chunk(int images) { qb200::g_rows_chunk = images; }
+int qb200_conv_rows_chunk(const qb200_conv_shape* s) {
+    if (!s || qb200::validate_shape(s)) return 0;
+    return qb200::rows_chunk_images(*s, nullptr);
+}
+
 void qb200_set_conv_algo(int algo) { qb200::g_conv_algo = algo; }
 int qb200_get_conv_algo(void) { return qb200::g_conv_algo; }
 
@@ -187,6 +216,26 @@ int qb200_quantconv2d_fused_ex(const qb200_conv_shape* s, const float* x, const 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // (a residual tail needs 32 more live registers in the epilogue than the 608-thread fused-quantize kernel has)
     const qb200::ConvGeom g0 = make_geom(*s);
+    if (const int chunk = rows_chunk_images(*s, tail)) {
+        // im2col-rows layer in L2-sized chunks of images (see g_rows_chunk): same kernels, same bits, less DRAM traffic
+        const int64_t in_img = (int64_t)s->C * s->H * s->W, out_img = (int64_t)s->K * g0.P * g0.Q;
+        for (int n0 = 0; n0 < s->N; n0 += chunk) {
+            qb200_conv_shape sc = *s;
+            sc.N = s->N - n0 < chunk ? s->N - n0 : chunk;
+            qb200_conv_tail tc;
+            if (tail) {
+                tc = *tail;
+                if (tc.residual) tc.residual += n0 * out_img;
+            }
+            if (int rc = quantize_input(&sc, x + n0 * in_img, aq, static_cast<uint8_t*>(workspace), st)) return rc;
+            void* out_c = out_kind == QB200_OUT_ACC ? static_cast<void*>(static_cast<int32_t*>(out) + n0 * out_img)
+                                                    : static_cast<void*>(static_cast<float*>(out) + n0 * out_img);
+            if (int rc = run_conv(&sc, static_cast<const uint8_t*>(workspace), true, prepared, w_scale, n_w_scale, bias, aq, out_c,
+                                  out_kind, st, nullptr, tail ? &tc : nullptr))
+                return rc;
+        }
+        return 0;
+    }
     if (dw_single_kernel(g0) && !(tail && tail->next_shape))   // (the depthwise kernel has the residual / ReLU tail)
         return run_conv(s, nullptr, false, prepared, w_scale, n_w_scale, bias, aq, out, out_kind, st, x, tail);
     if (single_kernel(g0, x) && !dw_single_kernel(g0) && !(tail && (tail->residual || tail->next_shape)))

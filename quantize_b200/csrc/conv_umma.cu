@@ -124,12 +124,24 @@ struct UmmaParams {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 16-byte shared-memory load through the shared window (the epilogue's constant tables; a plain dereference of a pointer
-// that may point at one of two tables compiled to generic loads)
+// Shared-memory loads through the shared window.  The epilogue's constant tables live in dynamic shared memory behind
+// pointers the compiler cannot classify: a plain dereference compiles to a GENERIC load (LD.E), which (a) has several
+// times the latency of LDS and (b) may alias the global stores of the epilogue, so it is never hoisted above them — the
+// ncu source page of round 2 showed every 4-column group of every epilogue stalled on two such loads (50 % of all
+// samples of the conv kernel on `long_sb`).  These wrappers are volatile without a memory clobber: ordered against the
+// barrier / TMEM instructions, free to move across ordinary stores.
 __device__ __forceinline__ float4 lds4(const float* p) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
     return v;
+}
+__device__ __forceinline__ float lds1(const float* p) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)));
+    return v;
+}
+__device__ __forceinline__ void sts2(void* p, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(a), "r"(b) : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -607,10 +619,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             for (int cb = 0; cb < prm.cblocks; ++cb) {
                 mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
-                const float4* xt = reinterpret_cast<const float4*>(xring + (size_t)xs * x_bytes) + (pw * 8) * (kBM / 4) + lane;
+                const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes) + (pw * 8) * kBM + lane * 4;
                 float4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = xt[i * (kBM / 4)];
+                for (int i = 0; i < 8; ++i) v[i] = lds4(xt + i * kBM);      // explicit LDS.128 (a generic load has several times the latency)
                 uint32_t w[4][2];  // [pixel][word]
                 quant_tile<2>(v, w, qp);
                 // One arrival per WARP (after a warp sync), not per thread: every mbarrier arrival wakes the warps that
@@ -643,7 +655,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     const int px = (t + rot) & 3;
                     const int row = lane * 4 + px;
                     const int jj = j16 ^ ((row >> 1) & 3);
-                    *reinterpret_cast<uint2*>(sa + row * kFqKC + (jj << 4) + (half << 3)) = make_uint2(w[t][0], w[t][1]);
+                    sts2(sa + row * kFqKC + (jj << 4) + (half << 3), w[t][0], w[t][1]);
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
                 __syncwarp();
@@ -824,7 +836,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     __syncwarp();
                     const float* rs = res_s + cons_slot * kResChunkFloats + lane;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) rv[j] = rs[j * 32];
+                    for (int j = 0; j < 32; ++j) rv[j] = lds1(rs + j * 32);
                     issue_one();   // into the slot of the PREVIOUS chunk, which every lane finished reading before the sync above
                     cons_slot = cons_slot == kResDepth - 1 ? 0 : cons_slot + 1;
                 } else if (has_res && row_ok) {
@@ -874,7 +886,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                                     const int32_t* t4 = wtab + (cc + j) * tbl;
                                     wsf = (float)(__ldg(t4 + i11) - __ldg(t4 + i01) - __ldg(t4 + i10) + __ldg(t4 + i00));
                                 }
-                                r[j] = tail(__fmaf_rn(sc[cc + j], __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]), br[cc + j]), j);
+                                r[j] = tail(__fmaf_rn(lds1(sc + cc + j), __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]), lds1(br + cc + j)), j);
                             }
                         }
                         if (kGroups == 1 && ep.store_f32) {   // (the two-group instantiation is launched for int8-only output)
@@ -911,34 +923,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
                     // kTail is a compile-time switch so that the plain op pays nothing for the optional fused tail.
-                    auto fast = [&](auto kTailTag) {
+                    // The constants of kPre column groups are fetched (LDS) before they are needed: all 8 groups of the
+                    // chunk where registers allow it, 2 groups in the instantiations with 576 / 608 threads.
+                    auto fast = [&](auto kTailTag, auto kZeroTag) {
                         constexpr bool kTail = decltype(kTailTag)::value;
-                        if (es.z_a == 0.f) {
+                        constexpr bool kZ = decltype(kZeroTag)::value;     // activation zero point != 0
+                        constexpr int kPre = (kFQ || kGroups > 1) ? 2 : (kZ ? 4 : 8);
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                                const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
-                                float r0 = __fmaf_rn(s4.x, (float)(int32_t)v[j + 0], b4.x);
-                                float r1 = __fmaf_rn(s4.y, (float)(int32_t)v[j + 1], b4.y);
-                                float r2 = __fmaf_rn(s4.z, (float)(int32_t)v[j + 2], b4.z);
-                                float r3 = __fmaf_rn(s4.w, (float)(int32_t)v[j + 3], b4.w);
-                                if (kTail) { r0 = tail(r0, j); r1 = tail(r1, j + 1); r2 = tail(r2, j + 2); r3 = tail(r3, j + 3); }
-                                const int64_t jo = (int64_t)j * PQ;
-                                o[jo] = r0;
-                                o[jo + PQ] = r1;
-                                o[jo + 2 * (int64_t)PQ] = r2;
-                                o[jo + 3 * (int64_t)PQ] = r3;
+                        for (int g0 = 0; g0 < 8; g0 += kPre) {
+                            float4 S[kPre], B[kPre], Wz[kZ ? kPre : 1];
+#pragma unroll
+                            for (int g = 0; g < kPre; ++g) {
+                                S[g] = lds4(sc + cc + 4 * (g0 + g));
+                                B[g] = lds4(br + cc + 4 * (g0 + g));
+                                if constexpr (kZ) Wz[g] = lds4(wrow + cc + 4 * (g0 + g));
                             }
-                        } else {
 #pragma unroll
-                            for (int j = 0; j < 32; j += 4) {
-                                const float4 s4 = *reinterpret_cast<const float4*>(sc + cc + j);
-                                const float4 w4 = *reinterpret_cast<const float4*>(wrow + cc + j);
-                                const float4 b4 = *reinterpret_cast<const float4*>(br + cc + j);
-                                float r0 = __fmaf_rn(s4.x, __fmaf_rn(es.z_a, w4.x, (float)(int32_t)v[j + 0]), b4.x);
-                                float r1 = __fmaf_rn(s4.y, __fmaf_rn(es.z_a, w4.y, (float)(int32_t)v[j + 1]), b4.y);
-                                float r2 = __fmaf_rn(s4.z, __fmaf_rn(es.z_a, w4.z, (float)(int32_t)v[j + 2]), b4.z);
-                                float r3 = __fmaf_rn(s4.w, __fmaf_rn(es.z_a, w4.w, (float)(int32_t)v[j + 3]), b4.w);
+                            for (int g = 0; g < kPre; ++g) {
+                                const int j = 4 * (g0 + g);
+                                float a0 = (float)(int32_t)v[j + 0], a1 = (float)(int32_t)v[j + 1], a2 = (float)(int32_t)v[j + 2],
+                                      a3 = (float)(int32_t)v[j + 3];
+                                if constexpr (kZ) {
+                                    a0 = __fmaf_rn(es.z_a, Wz[g].x, a0);
+                                    a1 = __fmaf_rn(es.z_a, Wz[g].y, a1);
+                                    a2 = __fmaf_rn(es.z_a, Wz[g].z, a2);
+                                    a3 = __fmaf_rn(es.z_a, Wz[g].w, a3);
+                                }
+                                float r0 = __fmaf_rn(S[g].x, a0, B[g].x);
+                                float r1 = __fmaf_rn(S[g].y, a1, B[g].y);
+                                float r2 = __fmaf_rn(S[g].z, a2, B[g].z);
+                                float r3 = __fmaf_rn(S[g].w, a3, B[g].w);
                                 if (kTail) { r0 = tail(r0, j); r1 = tail(r1, j + 1); r2 = tail(r2, j + 2); r3 = tail(r3, j + 3); }
                                 const int64_t jo = (int64_t)j * PQ;
                                 o[jo] = r0;
@@ -948,8 +962,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             }
                         }
                     };
-                    if (any_tail) fast(std::true_type{});
-                    else fast(std::false_type{});
+                    if (es.z_a == 0.f) {
+                        if (any_tail) fast(std::true_type{}, std::false_type{});
+                        else fast(std::false_type{}, std::false_type{});
+                    } else {
+                        if (any_tail) fast(std::true_type{}, std::true_type{});
+                        else fast(std::false_type{}, std::true_type{});
+                    }
                 } else if (acc_out) {
                     int32_t* o = static_cast<int32_t*>(out) + o_off;
 #pragma unroll
@@ -964,17 +983,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         if (k >= g.K) continue;
                         float r;
                         if (es.z_a == 0.f) {
-                            r = __fmaf_rn(sc[cc + j], (float)(int32_t)v[j], br[cc + j]);
+                            r = __fmaf_rn(lds1(sc + cc + j), (float)(int32_t)v[j], lds1(br + cc + j));
                         } else {
                             float wsf;
                             if (use_cls) {
-                                wsf = wrow[cc + j];
+                                wsf = lds1(wrow + cc + j);
                             } else {
                                 const int32_t* t4 = wtab + (cc + j) * tbl;
                                 wsf = (float)(__ldg(t4 + i11) - __ldg(t4 + i01) - __ldg(t4 + i10) + __ldg(t4 + i00));
                             }
                             const float t = __fmaf_rn(es.z_a, wsf, (float)(int32_t)v[j]);
-                            r = __fmaf_rn(sc[cc + j], t, br[cc + j]);
+                            r = __fmaf_rn(lds1(sc + cc + j), t, lds1(br + cc + j));
                         }
                         o[(int64_t)j * PQ] = tail(r, j);
                     }
@@ -1098,7 +1117,13 @@ bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
 // single 64-channel k-block, or at least twice as many input as output channels) and each image has >= 7 tiles; layers
 // with several channel tiles would quantize the same pixels once per channel tile, and 14x14 / 7x7 layers are ring-
 // latency bound, so those keep the standalone quantizer.
-bool umma_fused_quant_profitable(const ConvGeom& g) { return g.H * g.W >= 784 && (g.C == 64 || g.C >= 2 * g.K); }
+// Round 2 (A/B over all 53 layers with the fused variant forced): 1024 -> 256 at 14x14 also wins (72 vs 78 us); layers with
+// several channel tiles (128 -> 512: 113 vs 108 us, 256 -> 1024: 80 vs 72 us) lose because every channel tile quantizes
+// the same pixels again.
+bool umma_fused_quant_profitable(const ConvGeom& g) {
+    if (g.H * g.W >= 784) return g.C == 64 || g.C >= 2 * g.K;
+    return g.H * g.W >= 196 && g.C >= 4 * g.K;
+}
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo) {

@@ -348,3 +348,36 @@ def test_act_quantize_random_quantizers_match_the_ieee_sequence():
         capi.check(L.qb200_act_quantize_nhwc(x.data_ptr(), N, C, H, W, ctypes.byref(aq), out.data_ptr(), None), "act_quantize")
         want = torch.clamp(torch.round(x / scale - zero), qmin, qmax).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
         assert torch.equal(out, want), (it, s, z, qmin, qmax)
+
+
+# ---------------------------------------------------------------------------------------------------
+# band quantizer (round 2): planes with H*W % 4 != 0 and sub-sampled inputs of strided 1x1 layers
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(3, 512, 7, 7), (2, 2048, 7, 7), (2, 96, 7, 7), (5, 3, 7, 7), (2, 40, 9, 9), (1, 64, 15, 15),
+                                   (2, 24, 27, 27), (3, 32, 5, 3), (1, 7, 1, 3), (2, 64, 19, 21)])
+def test_act_quantize_band_kernel_planes(shape):
+    rng = np.random.default_rng(sum(shape) + 7)
+    x = (rng.standard_normal(shape) * 3).astype(np.float32)
+    for (s, z, lo, hi) in ((0.0371, -107.9, 0, 255), (1.0 / 3.0, -8.164, 0, 15), (0.02, -3.3, 2, 200)):
+        aq = ActQ(s, z, lo, hi)
+        want = oracle.act_quantize(x, s, z, lo, hi).astype(np.uint8)
+        N, C, H, W = shape
+        for off in (0, 1):       # off = 1: a base pointer that is only 4-byte aligned (4-byte cp.async path)
+            buf = torch.zeros(x.size + 4, dtype=torch.float32, device="cuda")
+            xt = buf[off:off + x.size].view(shape)
+            xt.copy_(torch.from_numpy(x))
+            q = c_act_quantize(xt, aq).cpu().numpy()
+            assert np.array_equal(q[..., :C], want.transpose(0, 2, 3, 1)), (shape, off)
+            assert not q[..., C:].any()
+
+
+@pytest.mark.parametrize("cfg", [(2, 256, 14, 14, 64, 2), (3, 96, 28, 28, 48, 2), (2, 64, 7, 7, 32, 2), (2, 40, 15, 13, 24, 2),
+                                 (1, 128, 56, 56, 64, 2), (2, 32, 12, 12, 16, 3), (2, 1024, 14, 14, 64, 2)])
+def test_strided_1x1_through_the_band_quantizer(cfg):
+    """1x1 / stride s / pad 0: the quantizer writes only the sampled pixels; int32 accumulators bit-exact vs the oracle."""
+    N, C, H, W, K, stride = cfg
+    c = random_conv_case(sum(cfg), N, C, H, W, K, 1, stride, 0)
+    acc, out = run_case(c, ALGOS["umma"])
+    qa, acc_ref, out_ref = oracle_case(c)
+    assert np.array_equal(acc.cpu().numpy(), acc_ref)
+    assert_close_1e3(out.cpu().numpy(), out_ref)

@@ -84,7 +84,9 @@ def test_argument_errors_match_reference(engine):
         engine.quantconv2d_float_input(T["x"].transpose(2, 3), T["packed"], T["des"], T["w_scale"], T["w_zero"], None, 1, 1)
     with pytest.raises(RuntimeError, match="weight must be a CUDA tensor"):
         engine.quantconv2d_float_input(T["x"], T["packed"].cpu(), T["des"], T["w_scale"], T["w_zero"], None, 1, 1)
-    with pytest.raises(RuntimeError, match="outside the hot path"):   # still-unbuilt ops raise instead of falling back
+    with pytest.raises(RuntimeError, match="outside the quantized-operator path"):   # the float ops are not part of this engine
+        engine.linear(T["x"].reshape(2, -1), T["x"].reshape(2, -1))
+    with pytest.raises(RuntimeError, match="must be packed uint8 tensors"):
         engine.quantlinear(T["x"], T["des"], T["w_scale"], T["w_zero"], T["packed"], T["des"], T["w_scale"], T["w_zero"], None)
 
 
