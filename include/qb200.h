@@ -131,7 +131,8 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
 #define QB200_ALGO_AUTO 0   /* tcgen05 implicit GEMM when groups == 1, CUDA-core kernel otherwise       */
 #define QB200_ALGO_DIRECT 1 /* CUDA-core direct conv (any groups)                                      */
 #define QB200_ALGO_UMMA 2   /* TMA im2col + tcgen05.mma kind::i8 + TMEM accumulators (groups == 1)      */
-#define QB200_ALGO_UMMA_TWO_KERNELS 3 /* as 2, plain variant only: quantizer kernel + im2col-TMA conv kernel (A/B tests) */
+#define QB200_ALGO_UMMA_TWO_KERNELS 3 /* as 2, plain variant only: quantizer kernel + im2col-TMA conv kernel, one CTA per tile
+                                       * (no fused-quantize / halo / CTA-pair variants; A/B tests) */
 #define QB200_ALGO_UMMA_FUSED_QUANT 4 /* as 2, and use the fused-quantize / halo variants wherever supported (tests)    */
 /* Every mbarrier wait of the tensor-core kernel is bounded (~4 s): on expiry the kernel records which wait it was
  * (1 TMA producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue, 5-7 fused-quantize producers) and traps instead of

@@ -136,7 +136,8 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
     if (from_ws && workspace_is_padded(g) && L.tapKC) return launch_conv_umma(g, q, wq + L.wtap_off, ep, out, st, 0, nullptr, nullptr, true);
     const ConvGeom gk = (from_ws && uses_subsampled_input(g)) ? subsampled_geom(g) : g;
-    if (resolve_algo(g) == QB200_ALGO_UMMA) return launch_conv_umma(gk, q, wq, ep, out, st);
+    if (resolve_algo(g) == QB200_ALGO_UMMA)
+        return launch_conv_umma(gk, q, wq, ep, out, st, 0, nullptr, nullptr, false, g_conv_algo != QB200_ALGO_UMMA_TWO_KERNELS);
     return launch_conv_direct(gk, q, wq, ep, out, st);
 }
 

@@ -112,6 +112,7 @@ struct UmmaParams {
     int res_async;          // residual tail: stream the identity tensor through a per-warp cp.async ring
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
     int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
+    int a_tiled;       // 1x1 / stride 1 / pad 0 main loop: A is the plain matrix [N*H*W][Cp], fetched with TILED 2-D TMA boxes
     const float* x;
     const float* q_scale;
     const float* q_zero;
@@ -238,6 +239,40 @@ __device__ __forceinline__ void tma_load_im2col_4d(void* dst, const CUtensorMap*
           "h"(off_w), "h"(off_h)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: the completion is signalled on a barrier given by its shared::cluster address (the
+//      leader CTA's), proven on hardware by tests/native/umma_pair.cu ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c, int w, int h,
+                                                        int n, uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c), "r"(w), "r"(h), "r"(n),
+          "h"(off_w), "h"(off_h)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -284,6 +319,32 @@ __device__ __forceinline__ void umma_i8_lohi(uint32_t tmem_d, uint32_t a_lo, uin
         "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
         : "memory");
+}
+// CTA pair: M = 256 (128 rows per CTA), each CTA holds half of the B tile; issued by the leader for both
+__device__ __forceinline__ void umma_i8_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], da, db, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(desc_hi)
+        : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -332,7 +393,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // kRagged: K is not a multiple of the channel tile; raggedness is then resolved per 32-column chunk (chunks past K are
 // skipped, only a partially valid chunk takes the per-element path).  A separate instantiation because the per-chunk
 // checks cost the common kernels 10 % on output-heavy layers (register pressure in the epilogue).
-template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1, bool kRagged = false>
+// kPair: CTA-pair variant for deep reductions (tcgen05.mma.cta_group::2).  Two CTAs of a cluster compute a 256-pixel x BN
+// tile: each stages its own 128 im2col rows and HALF of the weight tile (BN / 2 rows); the pair's tensor cores read both
+// halves, so the operand bytes per MAC drop by a third (128 + 128 instead of 128 + 256 rows per CTA and k-block) — deep
+// 3x3 layers are bound by exactly that L2 -> SM feed (ncu round 2: 9.3 TB/s of operand traffic at 37 % tensor-pipe
+// activity).  Protocol as in tests/native/umma_pair.cu: both producers signal the LEADER's full barrier (cluster-scope TMA
+// completion, the leader arms it with the bytes of both CTAs); the leader issues every MMA and its commits arrive, multicast,
+// on the stage-empty / accumulator-full barriers of both CTAs; every epilogue warp of the pair arrives on the leader's
+// accumulator-empty barrier.  Supported for the plain im2col main loop (not the halo / fused-quantize variants).
+template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1, bool kRagged = false, bool kPair = false>
 __global__ void __launch_bounds__(kFQ ? kThreadsFq : 64 + kGroups * kEpiWarps * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
@@ -342,8 +411,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const ConvGeom& g = prm.g;
     const ConvGeom& gm = prm.gm;
     const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
-    const bool halo = !kFQ && prm.halo != 0;
-    const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = BN * KC,
+    static_assert(!kPair || (!kFQ && kGroups == 1), "the CTA-pair variant covers the plain main loop");
+    const bool halo = !kFQ && !kPair && prm.halo != 0;
+    const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+    const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = (kPair ? BN / 2 : BN) * KC,
                    stage_bytes = halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes;
     uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [x_stages][KC][128] fp32
     const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u);  // ring slot size
@@ -361,7 +432,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int total_tiles = prm.m_tiles * prm.n_tiles;
+    // work units: tiles, round-robin over the CTAs — or, for the pair variant, 256-pixel pair tiles over the CTA pairs
+    const int total_tiles = kPair ? ((prm.m_tiles + 1) >> 1) * prm.n_tiles : prm.m_tiles * prm.n_tiles;
+    const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     const int kblocks = gm.R * gm.S * prm.cblocks;
 
     if (warp == 0 && lane == 0) {
@@ -373,7 +447,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         for (int i = 0; i < kMaxAcc; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], kEpiWarps);
+            mbar_init(&acc_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs
         }
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&xfull[i], 1);
@@ -381,9 +455,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 1) {
+        if constexpr (kPair) tmem_alloc_pair(tmem_slot, kTmemCols);
+        else tmem_alloc(tmem_slot, kTmemCols);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();   // the peer's barriers must be initialised before anything can signal them
+    else __syncthreads();
     // everything above touched only shared memory, TMEM and kernel parameters: it may overlap the previous kernel's tail
     pdl_launch_dependents();
     pdl_wait();
@@ -429,9 +507,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             }
-            for (int tile = blockIdx.x; !halo && tile < total_tiles; tile += gridDim.x) {
+            for (int tile = unit0; !halo && tile < total_tiles; tile += unit_step) {
                 const int n_tile = tile % prm.n_tiles;
-                const int m_tile = tile / prm.n_tiles;
+                // pair: this CTA loads the rows of m-tile 2 * (pair tile) + rank; an odd tail re-loads the last tile
+                const int m_tile = kPair ? min(2 * (tile / prm.n_tiles) + (int)pair_rank, prm.m_tiles - 1) : tile / prm.n_tiles;
                 const int64_t m0 = (int64_t)m_tile * kBM;
                 const int img = (int)(m0 / PQ);
                 const int rem = (int)(m0 - (int64_t)img * PQ);
@@ -443,11 +522,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             mbar_wait<kFQ ? 200 : 0>(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
+                            if constexpr (kPair) {
+                                // both CTAs' loads complete on the LEADER's barrier, armed with the bytes of both
+                                const uint32_t lead_bar = mapa_u32(smem_u32(&full[stage]), 0);
+                                if (pair_rank == 0) mbar_expect_tx(&full[stage], 2 * stage_bytes);
+                                if (prm.a_tiled) tma_load_2d_pair(sa, &tmap_a, lead_bar, cb * KC, (int)m0);
+                                else tma_load_im2col_4d_pair(sa, &tmap_a, lead_bar, cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
+                                tma_load_2d_pair(sb, &tmap_b, lead_bar, (r * gm.S + s) * gm.Cp + cb * KC,
+                                                 n_tile * BN + (int)pair_rank * (BN / 2));
+                                if (++stage == stages) { stage = 0; phase ^= 1; }
+                                continue;
+                            }
                             if (kFQ) {
                                 mbar_expect_tx(&full[stage], b_bytes);
                             } else {
                                 mbar_expect_tx(&full[stage], stage_bytes);
-                                tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
+                                if (prm.a_tiled) tma_load_2d(sa, &tmap_a, &full[stage], cb * KC, (int)m0);
+                                else tma_load_im2col_4d(sa, &tmap_a, &full[stage], cb * KC, cw, ch, img, (uint16_t)s, (uint16_t)r);
                             }
                             tma_load_2d(sb, &tmap_b, &full[stage], (r * gm.S + s) * gm.Cp + cb * KC, n_tile * BN);
                             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -472,7 +563,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int stage = 0, buf = 0, hs = 0;
         uint32_t phase = 0, acc_phase = 0, hphase = 0;
         uint32_t stage_lo = base16;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = unit0; tile < total_tiles && pair_rank == 0; tile += unit_step) {   // (pair: the leader issues for both)
             mbar_wait<kFQ ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * prm.acc_stride);
@@ -548,7 +639,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait<kFQ ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (kPair) {
+                        if (lane == 0) {
+                            const uint32_t a0 = stage_lo | lo_flag, b0 = (stage_lo + a16) | lo_flag;
+                            for (int k = 0; k < n_mma; ++k)
+                                umma_i8_lohi_pair(tmem_d, a0 + 2 * k, b0 + 2 * k, desc_hi, idesc, k ? 1u : accumulate);
+                            umma_commit_pair(&empty[stage]);   // the slot is reusable in BOTH CTAs
+                        }
+                    } else if (lane == 0) {
                         const uint32_t a0 = stage_lo | lo_flag, b0 = (stage_lo + a16) | lo_flag;
                         if (n_mma == 4) {          // KC = 128
                             umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
@@ -568,7 +666,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
                 }
             }
-            if (lane == 0) umma_commit(&acc_full[buf]);  // accumulator complete
+            if (lane == 0) {                                       // accumulator complete
+                if constexpr (kPair) umma_commit_pair(&acc_full[buf]);
+                else umma_commit(&acc_full[buf]);
+            }
             __syncwarp();
             if (++buf == prm.n_acc) { buf = 0; acc_phase ^= 1; }
         }
@@ -728,12 +829,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         const int acc_shift = prm.n_acc == 4 ? 2 : 1;
         int iter = 0;
-        for (int tile = blockIdx.x + grp * (int)gridDim.x, it = grp; tile < total_tiles;
-             tile += kGroups * (int)gridDim.x, it += kGroups, ++iter) {
+        const uint32_t acc_empty_lead = kPair ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;   // the leader's barriers
+        for (int tile = unit0 + grp * unit_step, it = grp; tile < total_tiles;
+             tile += kGroups * unit_step, it += kGroups, ++iter) {
             const int buf = it & (prm.n_acc - 1);                       // the MMA warp fills the buffers in tile order
             const uint32_t acc_phase = (uint32_t)(it >> acc_shift) & 1u;
-            const int m_tile = prm.fd_ntiles.div(tile);
-            const int n_tile = tile - m_tile * prm.n_tiles;
+            const int u_tile = prm.fd_ntiles.div(tile);                 // m-tile, or pair of m-tiles
+            const int n_tile = tile - u_tile * prm.n_tiles;
+            const int m_tile = kPair ? 2 * u_tile + (int)pair_rank : u_tile;   // (an odd tail: m_tile == m_tiles, no valid rows)
             const int k_base = n_tile * BN;
             // ---- per-tile channel constants (once per CTA when there is a single channel tile) ----
             float* sc = consts + (prm.n_tiles > 1 ? (iter & 1) : 0) * kConstFloats;   // two constant buffers, by tile parity
@@ -1001,14 +1104,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (lane == 0) {
+                if constexpr (kPair) mbar_arrive_cluster(acc_empty_lead + (uint32_t)buf * 8u);
+                else mbar_arrive(&acc_empty[buf]);
+            }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync_all();   // no CTA of the pair may exit while its partner can still signal its barriers
+    else __syncthreads();
     tc_fence_after();
-    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 1) {
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1105,6 +1215,33 @@ bool umma_halo_supported(const ConvGeom& g) {
 // adds a wave (14x14).
 bool umma_halo_profitable(const ConvGeom& g) { return g.Cp == 64 && g.P * g.Q >= 784; }
 
+// CTA-pair variant (cta_group::2): deep reductions, whose main loop is bound by the L2 -> SM operand feed.  Needs whole
+// channel tiles (the plain epilogue) and at least one pair of pixel tiles.  QB200_PAIR=0 turns it off (A/B measurements).
+bool umma_pair_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("QB200_PAIR");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+// Measured per layer on ResNet-50 at batch 256 (profiles/README.md, round 2): the pair variant is a few percent faster on
+// the spatial kernels with 256-wide channel tiles (3x3 @14: 37.5 -> 36.3 us, 3x3 @7: 42.0 -> 41.3, strided 3x3: 39.4 ->
+// 37.3, 42.5 -> 40.9) and SLOWER with 128-wide tiles (3x3 @28, K = 128: 46.5 -> 53.7) and on deep 1x1 layers (41.6 ->
+// 47.6): the main loop turned out to be bound by the latency of the stage ring (no unit above 46 % in ncu), not by the
+// operand bytes the pair saves, and the cross-CTA barrier hops add to that latency.  The GEMM probe
+// (tests/native/umma_pair.cu) shows the same ceiling: 2.47 -> 2.99 POPS at 8192^3.
+bool umma_pair_profitable(const ConvGeom& gm, int K, int m_tiles, int min_kgemm) {
+    const int64_t k_gemm = (int64_t)gm.R * gm.S * gm.Cp;
+    return umma_pair_enabled() && gm.R * gm.S > 1 && k_gemm >= min_kgemm && K % 256 == 0 && m_tiles >= 2;
+}
+int umma_pair_min_kgemm() {
+    static const int v = [] {
+        const char* e = getenv("QB200_PAIR_MIN_K");
+        return e ? atoi(e) : 2048;
+    }();
+    return v;
+}
+
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
     return umma_supported(g) && g.R == 1 && g.S == 1 && g.stride == 1 && g.pad == 0 && (g.H * g.W) % 4 == 0 &&
            g.C % 64 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
@@ -1126,7 +1263,8 @@ bool umma_fused_quant_profitable(const ConvGeom& g) {
 }
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
-                     cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo) {
+                     cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo,
+                     bool allow_pair) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
     const bool fq = x_fused != nullptr;
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
@@ -1160,6 +1298,14 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.KC = fq ? kFqKC : (gm.Cp % 128 == 0) ? 128 : (gm.Cp % 64 == 0) ? 64 : 32;
     prm.cblocks = gm.Cp / prm.KC;
     prm.halo = halo ? 1 : 0;
+    {
+        static const bool tiled_ok = [] {
+            const char* e = getenv("QB200_A_TILED");
+            return !(e && e[0] == '0');
+        }();
+        prm.a_tiled = (tiled_ok && !fq && !halo && gm.R == 1 && gm.S == 1 && gm.stride == 1 && gm.pad == 0 &&
+                       (int64_t)gm.N * gm.H * gm.W < (1ll << 31)) ? 1 : 0;
+    }
     prm.Hp = g.H + 2 * g.pad;
     prm.Wp = g.W + 2 * g.pad;
     prm.halo_rows = kBM + (g.R - 1) * prm.Wp + (g.S - 1);
@@ -1172,7 +1318,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
     const int64_t k_gemm = (int64_t)gm.R * gm.S * gm.Cp;
-    if (k_gemm >= 1024 && !fq) {
+    // deep reductions on the plain main loop: a CTA pair per 256-pixel tile (cta_group::2), channel tile 256 (or 128)
+    const bool pair = allow_pair && !fq && !halo && ep.residual == nullptr &&
+                      umma_pair_profitable(gm, g.K, prm.m_tiles, umma_pair_min_kgemm()) && (g.K % 256 == 0 || g.K == 128);
+    if (pair) {
+        BN = g.K % 256 == 0 ? 256 : 128;
+    } else if (k_gemm >= 1024 && !fq) {
         // deep reductions are bound by the operand feed (L2 -> SM, ~40 GB/s per SM): per tile k_gemm * (128 + BN) bytes,
         // and a partly filled last wave costs a whole tile time.  Pick the tile width with the least waves * bytes.
         int best = BN;
@@ -1206,7 +1357,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
         else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
     }
-    const size_t stage_bytes = halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + BN) * prm.KC;
+    const size_t stage_bytes = halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC;
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
     prm.wcls_smem = 0;
     prm.n_rcls = prm.n_ccls = 0;
@@ -1236,7 +1387,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // residual tail: stream the identity through per-warp cp.async rings when 16-byte pieces line up (4 pixels of one
     // image and channel) and two operand stages still fit next to the 96 KB of rings
     prm.res_async = 0;
-    if (!fq && !halo && ep.residual != nullptr && ep.out_kind == QB200_OUT_F32 && (g.P * g.Q) % 4 == 0 &&
+    if (!fq && !halo && !pair && ep.residual != nullptr && ep.out_kind == QB200_OUT_F32 && (g.P * g.Q) % 4 == 0 &&
         reinterpret_cast<uintptr_t>(ep.residual) % 16 == 0 && prm.M < (1ll << 31) &&
         kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq)
         prm.res_async = 1;
@@ -1268,7 +1419,8 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.layout = prm.KC == 128 ? 2u : (prm.KC == 64 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
     prm.sbo16 = (uint32_t)(8 * prm.KC) >> 4;
     // instruction descriptor: D=s32, A=u8, B=s8|u8, both K-major, N>>3, M>>4
-    prm.idesc = (2u << 4) | (0u << 7) | ((g.w_sign ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+    prm.idesc = (2u << 4) | (0u << 7) | ((g.w_sign ? 1u : 0u) << 10) | ((uint32_t)(BN >> 3) << 17) |
+                ((uint32_t)((pair ? 2 * kBM : kBM) >> 4) << 24);
     prm.err_flag = watchdog_flag();
     prm.x = x_fused;
     prm.q_scale = fq ? aq_fused->scale : nullptr;
@@ -1290,6 +1442,16 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(halo) failed with CUresult %d", (int)r);
+    } else if (!fq && prm.a_tiled) {
+        // 1x1 / stride 1 / pad 0: the im2col matrix IS the activation matrix [N*H*W rows][Cp bytes]; tiled boxes of 128 rows
+        cuuint64_t dims[2] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.N * gm.H * gm.W};
+        cuuint64_t strides[1] = {(cuuint64_t)gm.Cp};
+        cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)kBM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = api.tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(qa), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(1x1 activations) failed with CUresult %d", (int)r);
     } else if (!fq) {
         // activations: (C, W, H, N) u8, im2col mode; base pixel of an output (p,q) is (q*stride - pad, p*stride - pad)
         cuuint64_t dims[4] = {(cuuint64_t)gm.Cp, (cuuint64_t)gm.W, (cuuint64_t)gm.H, (cuuint64_t)gm.N};
@@ -1320,7 +1482,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         // weights: [K rows][R*S*Cp bytes], tiled mode, rows beyond K zero-filled
         cuuint64_t dims[2] = {(cuuint64_t)gm.R * gm.S * gm.Cp, (cuuint64_t)g.K};
         cuuint64_t strides[1] = {(cuuint64_t)gm.R * gm.S * gm.Cp};
-        cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)BN};
+        cuuint32_t box[2] = {(cuuint32_t)prm.KC, (cuuint32_t)(pair ? BN / 2 : BN)};   // pair: each CTA stages half of the tile
         cuuint32_t estr[2] = {1, 1};
         CUresult r = api.tiled(&tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(wq), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -1344,10 +1506,22 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         if (cur_dev >= 0 && cur_dev < 64) smem_set_mask.fetch_or(1ull << cur_dev, std::memory_order_release);
     }
     const int total_tiles = prm.m_tiles * prm.n_tiles;
     const int grid = total_tiles < sms ? total_tiles : sms;
+    if (pair) {
+        const int pair_tiles = ((prm.m_tiles + 1) / 2) * prm.n_tiles;
+        const int pgrid = 2 * (pair_tiles < sms / 2 ? pair_tiles : sms / 2);
+        if (ep.q8_out != nullptr)
+            QB_CUDA(launch_pdl_cluster(conv_umma_kernel<false, false, true, 1, false, true>, dim3(pgrid), dim3(kThreads), smem, st, 2, tmap_a, tmap_b, prm, out));
+        else
+            QB_CUDA(launch_pdl_cluster(conv_umma_kernel<false, false, false, 1, false, true>, dim3(pgrid), dim3(kThreads), smem, st, 2, tmap_a, tmap_b, prm, out));
+        QB_LAUNCH_CHECK();
+        return 0;
+    }
     if (fq) {
         // fp32 input as (pixels, channels, images); box = 128 pixels x 64 channels, no swizzle, zero fill past H*W
         cuuint64_t dims[3] = {(cuuint64_t)g.H * g.W, (cuuint64_t)g.C, (cuuint64_t)g.N};

@@ -241,7 +241,7 @@ static void make_map(EncodeTiledFn enc, CUtensorMap* m, void* p, int rows, int K
 }
 
 template <int CG>
-double run(EncodeTiledFn enc, int M, int N, int K, bool check, int reps, int* err_dev, int* err_host) {
+double run(EncodeTiledFn enc, int M, int N, int K, bool check, int reps, int* err_dev, int* err_host, int max_stages = 16) {
     std::vector<uint8_t> A((size_t)M * K);
     std::vector<int8_t> B((size_t)N * K);
     uint32_t s = 12345u + CG;
@@ -256,6 +256,7 @@ double run(EncodeTiledFn enc, int M, int N, int K, bool check, int reps, int* er
     make_map(enc, &tb, dB, N, K, BN / CG);
     const int stage_bytes = (BM + BN / CG) * KC;
     int stages = (200 * 1024) / stage_bytes; if (stages > 16) stages = 16;
+    if (stages > max_stages) stages = max_stages;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + 512;
     CK(cudaFuncSetAttribute(gemm_i8<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int sms = 0; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
@@ -318,6 +319,10 @@ int main(int argc, char** argv) {
     run<2>(enc, 1024, 768, 1024, true, 0, ed, eh);
     const double t1 = run<1>(enc, 8192, 8192, 8192, false, 5, ed, eh);
     const double t2 = run<2>(enc, 8192, 8192, 8192, false, 5, ed, eh);
+    if (argc > 3) {   // pipeline-depth sweep: is the main loop bound by bytes in flight?
+        for (int st = 2; st <= 4; ++st) run<1>(enc, 8192, 8192, 8192, false, 3, ed, eh, st);
+        for (int st = 2; st <= 6; ++st) run<2>(enc, 8192, 8192, 8192, false, 3, ed, eh, st);
+    }
     if (argc > 1) {
         FILE* o = fopen(argv[1], "w");
         if (o) {

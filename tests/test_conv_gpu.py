@@ -381,3 +381,32 @@ def test_strided_1x1_through_the_band_quantizer(cfg):
     qa, acc_ref, out_ref = oracle_case(c)
     assert np.array_equal(acc.cpu().numpy(), acc_ref)
     assert_close_1e3(out.cpu().numpy(), out_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CTA-pair variant (tcgen05.mma.cta_group::2, round 2): deep reductions
+# ---------------------------------------------------------------------------------------------------
+PAIR_CASES = [
+    # N, C, H, W, K, R, stride, pad
+    (2, 256, 14, 14, 256, 3, 1, 1),      # 3x3 @14: 4 pixel tiles, one channel tile
+    (3, 128, 28, 28, 128, 3, 1, 1),      # 19 pixel tiles: odd tail pair, channel tile 128
+    (5, 1024, 7, 7, 512, 1, 1, 0),       # 1x1 deep, two channel tiles, ragged last pixel tile
+    (2, 512, 7, 7, 512, 3, 1, 1),        # 3x3 @7 (the tensor-bound layer of ResNet-50)
+    (2, 128, 28, 28, 128, 3, 2, 1),      # strided 3x3
+    (2, 1024, 14, 14, 2048, 1, 2, 0),    # strided 1x1 over the sub-sampled buffer, 8 channel tiles
+    (9, 256, 9, 9, 768, 3, 1, 1),        # odd everything, 3 channel tiles
+]
+
+
+@pytest.mark.parametrize("cfg", PAIR_CASES)
+def test_cta_pair_deep_reductions(cfg):
+    """pair variant == one-CTA-per-tile variant == oracle: int32 accumulators bit-exact, fp32 bit-identical between the two
+    kernels (same epilogue arithmetic)."""
+    N, C, H, W, K, R, stride, pad = cfg
+    c = random_conv_case(sum(cfg) + 11, N, C, H, W, K, R, stride, pad)
+    acc_p, out_p = run_case(c, capi.ALGO_UMMA)        # the product's choice: deep reductions take the CTA-pair kernel
+    acc_1, out_1 = run_case(c, ALGOS["umma2k"])       # one CTA per tile
+    _, acc_ref, out_ref = oracle_case(c)
+    assert np.array_equal(acc_p.cpu().numpy(), acc_ref)
+    assert torch.equal(acc_p, acc_1) and torch.equal(out_p, out_1)
+    assert_close_1e3(out_p.cpu().numpy(), out_ref)
