@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--a-bits", type=int, default=8, help="activation bits (BASELINE headline: 8)")
     ap.add_argument("--sweep-out", default="", help="write the per-unique-shape layer sweep (SURVEY 8d config 5) as markdown")
     ap.add_argument("--graph", action="store_true", help="replay one CUDA-graph capture of the step instead of launching it")
+    ap.add_argument("--eager-e2e", action="store_true", help="e2e: launch the forward op by op instead of replaying CUDA graphs")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling record (global batch 256 / N per GPU)")
     ap.add_argument("--no-packing", action="store_true", help="skip the tensor_packing GB/s record")
     a = ap.parse_args()
@@ -554,7 +555,8 @@ def run_b200(args):
             torch.cuda.empty_cache()
             sspecs = models.conv_layer_specs(args.model, hi - lo)
             sstack = ConvStack(sspecs, device, seed=rank)
-            s_ms, _ = time_stack(torch, sstack, stream, K, max(args.warmup, 1), barrier, use_graph=args.graph)
+            # 32 images per GPU: ~1 ms of kernels behind ~100 launches — replayed from one CUDA graph
+            s_ms, _ = time_stack(torch, sstack, stream, K, max(args.warmup, 1), barrier, use_graph=True)
             s_ms_per_step = qdist.max_over_ranks(s_ms, device) / K
             del sstack
             torch.cuda.empty_cache()
@@ -563,6 +565,7 @@ def run_b200(args):
                   "ms_per_step": round(s_ms_per_step, 4),
                   # one GPU's rate on the full batch is what each rank of the weak run achieves: 256 / ms_per_step
                   "efficiency_vs_n1": round((s_value / n_gpus) / (PER_GPU_BATCH / (ms_per_step / 1e3)), 4),
+                  "launch": "stream launches" if world == 1 and not args.graph else "cuda graph replay",
                   "verify": verify}
 
     # ---- end to end through the public op API: host images -> logits on host ----------------------------
@@ -578,12 +581,27 @@ def run_b200(args):
         compute = torch.cuda.current_stream()
         copy_stream = torch.cuda.Stream(device=device)
 
+        from quantize_b200 import host as qhost
+
         def run_e2e(batch):
             """every step: H2D of its inputs (pinned host memory), forward, D2H of its logits; the H2D of step k+1 runs on
-            a copy stream into the second device buffer while step k computes.  Returns ms per step (device events)."""
+            a copy stream into the second device buffer while step k computes.  The forward is replayed from CUDA graphs
+            (host.GraphedForward: one graph per input buffer) unless --eager-e2e.  Returns ms per step (device events)."""
             host_in = torch.randn(batch, 3, hw, hw, generator=torch.Generator().manual_seed(100 + rank)).pin_memory()
             host_out = torch.empty(batch, n_classes, dtype=torch.float32).pin_memory()
-            dev_in = [torch.empty_like(host_in, device=device) for _ in range(2)]
+            L.qb200_launch_count_reset()
+            with torch.no_grad():
+                net(torch.zeros(batch, 3, hw, hw, device=device))
+            torch.cuda.synchronize()
+            launches_per_forward = int(L.qb200_launch_count())
+            graphed, why = None, None
+            if not args.eager_e2e:
+                try:
+                    graphed = qhost.GraphedForward(net, torch.zeros(batch, 3, hw, hw, device=device), n_buffers=2)
+                except Exception as ex:   # noqa: BLE001  (the eager path is the same computation)
+                    why = f"{type(ex).__name__}: {ex}"[:200]
+                    torch.cuda.synchronize()
+            dev_in = graphed.inputs if graphed is not None else [torch.empty_like(host_in, device=device) for _ in range(2)]
             ev_copied = [torch.cuda.Event() for _ in range(2)]
             ev_used = [torch.cuda.Event() for _ in range(2)]
 
@@ -599,8 +617,11 @@ def run_b200(args):
                     if k + 1 < n:
                         issue_copy(k + 1)
                     compute.wait_event(ev_copied[k % 2])
-                    with torch.no_grad():
-                        logits = net(dev_in[k % 2])
+                    if graphed is not None:
+                        logits = graphed(k % 2)
+                    else:
+                        with torch.no_grad():
+                            logits = net(dev_in[k % 2])
                     ev_used[k % 2].record(compute)
                     host_out.copy_(logits, non_blocking=True)
 
@@ -618,7 +639,6 @@ def run_b200(args):
             h2d_gbs = host_in.numel() * 4 * 3 / (c0.elapsed_time(c1) * 1e-3) / 1e9
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
-            L.qb200_launch_count_reset()
             wall0 = time.perf_counter()
             e0.record()
             steps(K)
@@ -626,9 +646,11 @@ def run_b200(args):
             barrier()
             wall = time.perf_counter() - wall0
             e_ms = qdist.max_over_ranks(e0.elapsed_time(e1), device)
-            return e_ms / K, wall / K * 1e3, host_in.numel() * 4, host_out.numel() * 4, int(L.qb200_launch_count()) // K, h2d_gbs
+            mode = "cuda graph replay (host.GraphedForward)" if graphed is not None else ("eager" + (f" (graph capture failed: {why})" if why else ""))
+            del graphed
+            return e_ms / K, wall / K * 1e3, host_in.numel() * 4, host_out.numel() * 4, launches_per_forward, h2d_gbs, mode
 
-        e_ms, wall_ms, h2d, d2h, e_launches, h2d_gbs = run_e2e(args.batch)
+        e_ms, wall_ms, h2d, d2h, e_launches, h2d_gbs, e_mode = run_e2e(args.batch)
         e2e = {"value": round(args.batch * n_gpus / (e_ms / 1e3), 1), "unit": "images/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": round(e_ms, 3), "wall_ms_per_step": round(wall_ms, 3),
@@ -638,6 +660,7 @@ def run_b200(args):
                       "quant_engine.quantconv2d_float_input / quantconv2d_chain (ReLU / residual add of each block run in the "
                       "conv epilogues; with chain_blocks the activations between the convs of a block stay int8)" % (not args.no_chain),
                "pipelining": "H2D of step k+1 (copy stream, double buffer) overlaps the forward of step k; all copies inside the timed region",
+               "launch": e_mode,
                "engine_launches_per_step": e_launches}
         if strong is not None:
             if world == 1:

@@ -134,6 +134,7 @@ int qb200_act_quantize_nhwc(const float* x, int32_t N, int32_t C, int32_t H, int
 #define QB200_ALGO_UMMA_TWO_KERNELS 3 /* as 2, plain variant only: quantizer kernel + im2col-TMA conv kernel, one CTA per tile
                                        * (no fused-quantize / halo / CTA-pair variants; A/B tests) */
 #define QB200_ALGO_UMMA_FUSED_QUANT 4 /* as 2, and use the fused-quantize / halo variants wherever supported (tests)    */
+#define QB200_ALGO_UMMA_PAIR 5        /* as 3, but the CTA-pair (tcgen05.mma.cta_group::2) variant wherever supported (tests) */
 /* Every mbarrier wait of the tensor-core kernel is bounded (~4 s): on expiry the kernel records which wait it was
  * (1 TMA producer, 2 MMA/accumulator, 3 MMA/operands, 4 epilogue, 5-7 fused-quantize producers) and traps instead of
  * hanging the GPU.  0 = never fired.  Readable after the trap (mapped host memory). */

@@ -25,7 +25,7 @@ SYMBOLS = [
 
 U8, I8, I16, I32, I64, F16, F32, F64, BF16 = range(9)
 OUT_F32, OUT_ACC = 0, 1
-ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA, ALGO_UMMA_TWO_KERNELS, ALGO_UMMA_FUSED_QUANT = 0, 1, 2, 3, 4
+ALGO_AUTO, ALGO_DIRECT, ALGO_UMMA, ALGO_UMMA_TWO_KERNELS, ALGO_UMMA_FUSED_QUANT, ALGO_UMMA_PAIR = 0, 1, 2, 3, 4, 5
 
 
 class ConvShape(ctypes.Structure):

@@ -24,6 +24,9 @@
 namespace qb200 {
 namespace {
 
+#ifndef QB200_VEC4_MIN_BLOCKS
+#define QB200_VEC4_MIN_BLOCKS 6   // 6 x 128 threads per SM (<= 85 registers): 105 registers left 4 blocks per SM, and the small
+#endif                            // layers (784 blocks for 256 ch @14x14) ran as 1.3 latency-bound waves (ncu, round 2)
 constexpr int kPix = 128;  // pixels per block
 constexpr int kThreads = 128;
 constexpr int kCw = 128;   // channel bytes per shared-memory pass
@@ -91,7 +94,7 @@ __device__ __forceinline__ void copy_out_padded(const uint4* tile, uint8_t* __re
 // ---------------------------------------------------------------------------------------------
 // vector kernel: H*W % 4 == 0, x 16-byte aligned.  thread = (pixel quad, 16-channel group)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, QB200_VEC4_MIN_BLOCKS)
 act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_pix, int C, int Cp, int HW,
                               const PadSpec ps, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
                               const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {

@@ -22,7 +22,7 @@ int g_rows_chunk = [] {
 int resolve_algo(const ConvGeom& g) {
     int algo = g_conv_algo;
     if (algo == QB200_ALGO_AUTO) algo = umma_supported(g) ? QB200_ALGO_UMMA : QB200_ALGO_DIRECT;
-    if (algo == QB200_ALGO_UMMA_TWO_KERNELS || algo == QB200_ALGO_UMMA_FUSED_QUANT) algo = QB200_ALGO_UMMA;
+    if (algo == QB200_ALGO_UMMA_TWO_KERNELS || algo == QB200_ALGO_UMMA_FUSED_QUANT || algo == QB200_ALGO_UMMA_PAIR) algo = QB200_ALGO_UMMA;
     return algo;
 }
 
@@ -32,14 +32,16 @@ bool dw_single_kernel(const ConvGeom& g) { return g_conv_algo == QB200_ALGO_AUTO
 
 bool single_kernel(const ConvGeom& g, const float* x) {
     if (dw_single_kernel(g)) return true;
-    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || resolve_algo(g) != QB200_ALGO_UMMA) return false;
+    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || g_conv_algo == QB200_ALGO_UMMA_PAIR || resolve_algo(g) != QB200_ALGO_UMMA) return false;
     if (!umma_fused_quant_supported(g, x)) return false;
     return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_fused_quant_profitable(g);
 }
 
 // stride-1 spatial kernels: zero-padded workspace + one halo load per tile instead of one im2col load per tap
 bool workspace_is_padded(const ConvGeom& g) {
-    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || resolve_algo(g) != QB200_ALGO_UMMA || !umma_halo_supported(g)) return false;
+    if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || g_conv_algo == QB200_ALGO_UMMA_PAIR || resolve_algo(g) != QB200_ALGO_UMMA ||
+        !umma_halo_supported(g))
+        return false;
     return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_halo_profitable(g);   // algo 4 forces every variant (tests)
 }  // (umma_halo_supported implies the tap-major weight copy exists: spatial kernel, groups == 1, C > 4)
 
@@ -137,7 +139,8 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     if (from_ws && workspace_is_padded(g) && L.tapKC) return launch_conv_umma(g, q, wq + L.wtap_off, ep, out, st, 0, nullptr, nullptr, true);
     const ConvGeom gk = (from_ws && uses_subsampled_input(g)) ? subsampled_geom(g) : g;
     if (resolve_algo(g) == QB200_ALGO_UMMA)
-        return launch_conv_umma(gk, q, wq, ep, out, st, 0, nullptr, nullptr, false, g_conv_algo != QB200_ALGO_UMMA_TWO_KERNELS);
+        return launch_conv_umma(gk, q, wq, ep, out, st, 0, nullptr, nullptr, false,
+                                g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS ? 0 : (g_conv_algo == QB200_ALGO_UMMA_PAIR ? 2 : 1));
     return launch_conv_direct(gk, q, wq, ep, out, st);
 }
 

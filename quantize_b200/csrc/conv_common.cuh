@@ -133,10 +133,11 @@ int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, 
 // x_fused != nullptr: 1x1 / stride-1 layer whose A operand is quantized inside the kernel from the fp32 NCHW input
 // (see umma_fused_quant_supported); qa is then ignored.
 // halo: qa is the zero-padded NHWC buffer written by launch_act_quantize_padded (see umma_halo_supported).
-// allow_pair: deep reductions may run as CTA pairs (tcgen05.mma.cta_group::2); false keeps one CTA per tile (A/B, tests).
+// pair_mode: CTA-pair variant (tcgen05.mma.cta_group::2) — 0 never, 1 where it was measured to win (deep spatial kernels
+// with 256-wide channel tiles), 2 wherever it is supported (tests).
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows = 0, const float* x_fused = nullptr,
-                     const qb200_act_quant* aq_fused = nullptr, bool halo = false, bool allow_pair = true);
+                     const qb200_act_quant* aq_fused = nullptr, bool halo = false, int pair_mode = 1);
 bool umma_halo_supported(const ConvGeom& g);
 bool umma_halo_profitable(const ConvGeom& g);
 int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);

@@ -1264,7 +1264,7 @@ bool umma_fused_quant_profitable(const ConvGeom& g) {
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo,
-                     bool allow_pair) {
+                     int pair_mode) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
     const bool fq = x_fused != nullptr;
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
@@ -1319,8 +1319,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
     const int64_t k_gemm = (int64_t)gm.R * gm.S * gm.Cp;
     // deep reductions on the plain main loop: a CTA pair per 256-pixel tile (cta_group::2), channel tile 256 (or 128)
-    const bool pair = allow_pair && !fq && !halo && ep.residual == nullptr &&
-                      umma_pair_profitable(gm, g.K, prm.m_tiles, umma_pair_min_kgemm()) && (g.K % 256 == 0 || g.K == 128);
+    // pair_mode 0: never, 1: where measured to win, 2: wherever the variant is supported (tests)
+    const bool pair_ok = !fq && !halo && ep.residual == nullptr && prm.m_tiles >= 2 && (g.K % 256 == 0 || g.K == 128);
+    const bool pair = pair_ok && (pair_mode == 2 || (pair_mode == 1 && umma_pair_profitable(gm, g.K, prm.m_tiles, umma_pair_min_kgemm())));
     if (pair) {
         BN = g.K % 256 == 0 ? 256 : 128;
     } else if (k_gemm >= 1024 && !fq) {

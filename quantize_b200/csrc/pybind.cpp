@@ -25,6 +25,7 @@
 #include <ATen/cuda/CUDAEvent.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <atomic>
 #include <list>
 #include <memory>
 #include <mutex>
@@ -194,6 +195,11 @@ struct PreparedWeights {
     // the buffer is written on the stream of the first call; other streams wait on this event before reading it
     std::shared_ptr<at::cuda::CUDAEvent> ready;
     cudaStream_t stream;
+    std::atomic<bool> settled{false};
+    PreparedWeights() = default;
+    PreparedWeights(PreparedWeights&& o) noexcept
+        : buffer(std::move(o.buffer)), zero_is_zero(o.zero_is_zero), ready(std::move(o.ready)), stream(o.stream),
+          settled(o.settled.load()) {}
 };
 
 std::mutex g_mu;   // guards the four caches below, nothing else
@@ -327,7 +333,12 @@ std::shared_ptr<PreparedWeights> prepared_weights(const qb200_conv_shape& s, con
         std::lock_guard<std::mutex> lock(g_mu);
         pw = g_prep_cache.insert(wk, weight, std::move(fresh));
     }
-    if (pw->stream != static_cast<cudaStream_t>(st)) pw->ready->block(at::cuda::getCurrentCUDAStream());
+    // first use on another stream: order it after the preparation (once the event has completed no wait is needed any
+    // more — this also keeps replays / stream captures free of cross-stream waits)
+    if (pw->stream != static_cast<cudaStream_t>(st) && !pw->settled.load(std::memory_order_acquire)) {
+        if (pw->ready->query()) pw->settled.store(true, std::memory_order_release);
+        else pw->ready->block(at::cuda::getCurrentCUDAStream());
+    }
     return pw;
 }
 

@@ -404,7 +404,7 @@ def test_cta_pair_deep_reductions(cfg):
     kernels (same epilogue arithmetic)."""
     N, C, H, W, K, R, stride, pad = cfg
     c = random_conv_case(sum(cfg) + 11, N, C, H, W, K, R, stride, pad)
-    acc_p, out_p = run_case(c, capi.ALGO_UMMA)        # the product's choice: deep reductions take the CTA-pair kernel
+    acc_p, out_p = run_case(c, capi.ALGO_UMMA_PAIR)   # the CTA-pair kernel wherever it is supported
     acc_1, out_1 = run_case(c, ALGOS["umma2k"])       # one CTA per tile
     _, acc_ref, out_ref = oracle_case(c)
     assert np.array_equal(acc_p.cpu().numpy(), acc_ref)
