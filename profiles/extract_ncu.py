@@ -9,6 +9,12 @@ NAMES = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram_
          "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
          "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
          "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+         "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.sum",
+         "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.per_cycle_elapsed",
+         "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.peak_sustained",
+         "TPC.TriageCompute.sm__pipe_tensor_subpipe_imma_cycles_active_realtime.avg",
+         "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__m_l1tex2xbar_write_bytes.sum",
+         "l1tex__m_xbar2l1tex_read_sectors.avg.pct_of_peak_sustained_elapsed",
          "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
          "smsp__average_warp_latency_issue_stalled_no_instruction.ratio", "smsp__average_warp_latency_issue_stalled_wait.ratio",
          "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_not_selected.ratio"]

@@ -160,6 +160,86 @@ act_quantize_nhwc_vec4_kernel(const float* __restrict__ x, uint8_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// stride-2 sub-sampling kernel (the input of a 1x1 / stride-2 / pad-0 layer: ResNet's down-sampling shortcuts).
+// Same machine mapping as the vector kernel, over the SAMPLED rows only: a thread owns 4 consecutive input pixels of a
+// sampled row (one 16-byte load per channel: a warp reads whole 512-byte runs) x 16 channels, and keeps pixels 0 and 2.
+// The scalar kernel reads every other 4-byte word with 16 loads in flight per thread: 2.3-3.5 TB/s of the bytes it
+// touches; this one reads the same sectors with 16-byte loads.  Needs W % 4 == 0 and a 16-byte aligned input.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+act_quantize_nhwc_sub2_kernel(const float* __restrict__ x, uint8_t* __restrict__ q, int64_t total_quads, int64_t total_out, int C,
+                              int Cp, int H, int W, int P, const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                              const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ uint4 tile[(kPix / 2) * (kCw / 16)];
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int pq = threadIdx.x & 31;   // quad inside the block
+    const int cg = threadIdx.x >> 5;   // 16-channel group inside a 64-channel sub-pass (warp-uniform)
+    const int W4 = W >> 2;
+    const int64_t gq = (int64_t)blockIdx.x * 32 + pq;
+    const int c_base = blockIdx.y * kCw;
+    const int cw = min(kCw, Cp - c_base);
+    const int chunks = cw >> 4;
+    const bool active = gq < total_quads;
+    int64_t n = 0;
+    int prow = 0, w4 = 0;
+    if (active) {
+        const int64_t per_img = (int64_t)P * W4;
+        n = gq / per_img;
+        const int rem = (int)(gq - n * per_img);
+        prow = rem / W4;
+        w4 = rem - prow * W4;
+    }
+    const int64_t HW = (int64_t)H * W;
+    for (int sub = 0; sub < chunks; sub += 4) {
+        const int j = sub + cg;
+        if (active && j < chunks) {
+            const int c0 = c_base + j * 16;
+            const float* xp = x + (n * C + c0) * HW + (int64_t)prow * 2 * W + w4 * 4;
+            float4 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = (c0 + i < C) ? ldg_stream4(xp + (int64_t)i * HW) : make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t w0[4], w1[4];   // output pixels 2*w4 and 2*w4 + 1 (input columns 4*w4 and 4*w4 + 2)
+            if (p.byte_clamp) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int a[4], b[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) quant_int2(v[4 * k + c].x, v[4 * k + c].z, p, a[c], b[c]);
+                    w0[k] = pack_clamp4<false>(a[0], a[1], a[2], a[3], p);
+                    w1[k] = pack_clamp4<false>(b[0], b[1], b[2], b[3], p);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    w0[k] = quant_word_exact(v[4 * k].x, v[4 * k + 1].x, v[4 * k + 2].x, v[4 * k + 3].x, p.s, p.z, p.lo, p.hi);
+                    w1[k] = quant_word_exact(v[4 * k].z, v[4 * k + 1].z, v[4 * k + 2].z, v[4 * k + 3].z, p.s, p.z, p.lo, p.hi);
+                }
+            }
+            if (c0 + 16 > C) {   // padded channels must be exactly 0 even when qmin > 0
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t keep = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (c0 + k * 4 + b < C) keep |= 0xFFu << (8 * b);
+                    w0[k] &= keep;
+                    w1[k] &= keep;
+                }
+            }
+            const int r0 = pq * 2, r1 = pq * 2 + 1;
+            tile[r0 * (kCw / 16) + (j ^ (r0 & 7))] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+            tile[r1 * (kCw / 16) + (j ^ (r1 & 7))] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+        }
+    }
+    __syncthreads();
+    const int64_t g0 = (int64_t)blockIdx.x * (kPix / 2);
+    const int n_rows = (int)min((int64_t)(kPix / 2), total_out - g0);
+    copy_out(tile, q, g0, n_rows, chunks, Cp, c_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic kernel: any H*W / alignment.  thread = one pixel, scalar (still warp-coalesced) loads
 // ---------------------------------------------------------------------------------------------
 // sub > 1: only the pixels (p*sub, q*sub) of each image are quantized, into a compact [N, P, Q, Cp] buffer — what a
@@ -602,6 +682,18 @@ int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb20
                "act_quantize: activation quantizer parameters missing");
     QB_REQUIRE(g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1, QB200_EINVAL, "act_quantize_subsampled: not a strided 1x1 layer");
     const int64_t total = (int64_t)g.N * g.P * g.Q;
+    static const bool sub2_ok = [] {
+        const char* e = getenv("QB200_SUB2_QUANT");
+        return !(e && e[0] == '0');
+    }();
+    if (sub2_ok && g.stride == 2 && g.W % 4 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0 && g.Q * 2 == g.W) {
+        const int64_t quads = (int64_t)g.N * g.P * (g.W / 4);
+        dim3 grid2((unsigned)ceil_div64(quads, 32), (unsigned)((g.Cp + kCw - 1) / kCw));
+        QB_CUDA(launch_pdl(act_quantize_nhwc_sub2_kernel, grid2, dim3(kThreads), 0, st, x, q, quads, total, g.C, g.Cp, g.H, g.W, g.P,
+                           aq->scale, aq->zero, aq->qmin, aq->qmax));
+        QB_LAUNCH_CHECK();
+        return 0;
+    }
     // (pad == 0 and R == 1: P = (H - 1) / stride + 1 = ceil(H / stride), what the band kernel derives)
     // measured (profiles/README.md, round 2): the band kernel LOSES on sub-sampled inputs (256ch @56 s2: 132 vs 116 us;
     // 1024ch @14 s2: 58 vs 49 us — 8-byte copies of half-used rows), so it is opt-in here

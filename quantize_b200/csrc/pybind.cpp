@@ -202,11 +202,13 @@ struct PreparedWeights {
           settled(o.settled.load()) {}
 };
 
-std::mutex g_mu;   // guards the four caches below, nothing else
-DerivedCache<std::vector<int64_t>> g_des_cache(4096);
-DerivedCache<PreparedWeights> g_prep_cache(2048);
-DerivedCache<at::Tensor> g_float_cache(4096);
-DerivedCache<std::pair<float, float>> g_range_cache(4096);
+// The caches hold CUDA tensors and events.  They are intentionally never destroyed: static destructors run after the CUDA
+// runtime has begun to shut down, and destroying an event of a second device there crashed the interpreter at exit.
+std::mutex& g_mu = *new std::mutex;   // guards the four caches below, nothing else
+auto& g_des_cache = *new DerivedCache<std::vector<int64_t>>(4096);
+auto& g_prep_cache = *new DerivedCache<PreparedWeights>(2048);
+auto& g_float_cache = *new DerivedCache<at::Tensor>(4096);
+auto& g_range_cache = *new DerivedCache<std::pair<float, float>>(4096);
 
 // Tensor::_version() throws for inference-mode tensors (torch.inference_mode()): they cannot be modified in place
 // outside inference mode, so the address alone identifies them.
@@ -265,7 +267,7 @@ const float* device_float(const QParam& q, const at::Device& dev, std::vector<at
         return v->data_ptr<float>();
     }
     // python number: one cached device scalar per (value, device)
-    static std::unordered_map<int64_t, at::Tensor> scalars;
+    static auto& scalars = *new std::unordered_map<int64_t, at::Tensor>;   // (never destroyed, see the caches above)
     float fv = (float)q.val;
     int32_t bits;
     memcpy(&bits, &fv, 4);
