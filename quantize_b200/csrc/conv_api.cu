@@ -30,8 +30,21 @@ int resolve_algo(const ConvGeom& g) {
 // depthwise layers: one fused CUDA-core kernel (product default; the explicit algo settings keep the two-kernel paths)
 bool dw_single_kernel(const ConvGeom& g) { return g_conv_algo == QB200_ALGO_AUTO && dw_fused_supported(g); }
 
+// few-channel 7x7-type stems: the grouped im2col rows are built in shared memory inside the tensor-core kernel (no
+// 617 MB round trip of the rows through HBM).  QB200_STEM_FUSED=0 keeps the two-kernel path (A/B measurements).
+bool stem_single_kernel(const ConvGeom& g, const float* x) {
+    static const bool on = [] {
+        const char* e = getenv("QB200_STEM_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    if (!on || g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || g_conv_algo == QB200_ALGO_UMMA_PAIR || resolve_algo(g) != QB200_ALGO_UMMA)
+        return false;
+    return umma_stem_supported(g, x);
+}
+
 bool single_kernel(const ConvGeom& g, const float* x) {
     if (dw_single_kernel(g)) return true;
+    if (stem_single_kernel(g, x)) return true;
     if (g_conv_algo == QB200_ALGO_UMMA_TWO_KERNELS || g_conv_algo == QB200_ALGO_UMMA_PAIR || resolve_algo(g) != QB200_ALGO_UMMA) return false;
     if (!umma_fused_quant_supported(g, x)) return false;
     return g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT || umma_fused_quant_profitable(g);
@@ -133,6 +146,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
         ep.store_f32 = out != nullptr;
     }
     if (x_fused && dw_single_kernel(g)) return launch_conv_dw_fused(g, x_fused, wq, ep, aq, out, st);
+    if (x_fused && stem_single_kernel(g, x_fused)) return launch_conv_umma(g, nullptr, wq + L.wcol_off, ep, out, st, L.Kcol, x_fused, aq);
     if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]

@@ -145,6 +145,9 @@ int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_ac
 int launch_zero_pad_borders(uint8_t* q, int N, int H, int W, int pad, int Cp, cudaStream_t st);
 bool umma_fused_quant_supported(const ConvGeom& g, const float* x);
 bool umma_fused_quant_profitable(const ConvGeom& g);
+// few-channel layer with grouped im2col rows (the 7x7 RGB stem): rows built in shared memory from the fp32 input
+// (launch_conv_umma with gemm_rows > 0 AND x_fused)
+bool umma_stem_supported(const ConvGeom& g, const float* x);
 // 1x1 / stride > 1 / pad 0: quantize only the pixels the conv reads into a compact [N, P, Q, Cp] buffer
 int launch_act_quantize_subsampled(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);
 static inline bool uses_subsampled_input(const ConvGeom& g) { return g.R == 1 && g.S == 1 && g.pad == 0 && g.stride > 1; }

@@ -98,6 +98,9 @@ struct UmmaParams {
     int wcls_smem;     // bytes of one class-table buffer (0: 4-corner lookups in the global prefix tables instead)
     int n_rcls, n_ccls;
     uint8_t rcls[kMaxCls][2], ccls[kMaxCls][2];   // [lo, hi) tap ranges
+    // closed form of the class index of output row p: min(p, cls_head_r) + max(0, p - cls_tail_r + 1) (columns alike);
+    // cls_fast = the host checked it against the enumeration
+    int cls_fast, cls_head_r, cls_tail_r, cls_head_c, cls_tail_c;
     int* err_flag;     // device int: set non-zero by the watchdog
     // fused-quantize variant (1x1, stride 1): A is produced from the fp32 NCHW input inside the kernel
     int tiles_per_img; // > 0: M tiles never straddle images (tile = image, 128-pixel block); 0: flat pixel tiling
@@ -113,6 +116,11 @@ struct UmmaParams {
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
     int tap_group;     // filter taps per weight stage (1, S or R*S): one 3-D TMA box of the tap-major weight copy
     int a_tiled;       // 1x1 / stride 1 / pad 0 main loop: A is the plain matrix [N*H*W][Cp], fetched with TILED 2-D TMA boxes
+    // fused stem (kStem): few-channel layer whose grouped im2col rows (conv_common.cuh: im2col8_row_bytes) are built in
+    // shared memory from the fp32 input — the rows never exist in HBM.  Per tile ONE 4-D TMA box [C][st_rows_box][W] of
+    // fp32 input rows (rows outside the image zero-filled) -> quantized byte planes [C][st_rows_box][st_Wq] (input column
+    // iw at byte st_margin + iw; margins stay 0 = the reference's zero padding) -> 8-byte windows of the planes.
+    int st_rows_box, st_Wq, st_margin, st_patch_bytes, st_plane_bytes, st_ring;
     const float* x;
     const float* q_scale;
     const float* q_zero;
@@ -279,6 +287,12 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int x, int y, int z, int w) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(w)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* map, int x, int y, int z) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z)
@@ -401,7 +415,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo1
 // completion, the leader arms it with the bytes of both CTAs); the leader issues every MMA and its commits arrive, multicast,
 // on the stage-empty / accumulator-full barriers of both CTAs; every epilogue warp of the pair arrives on the leader's
 // accumulator-empty barrier.  Supported for the plain im2col main loop (not the halo / fused-quantize variants).
-template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1, bool kRagged = false, bool kPair = false>
+// kStem (with kFQ): the quantizer warps build the grouped im2col rows of a few-channel layer (the 7x7 RGB stem) in shared
+// memory from fp32 input rows (UmmaParams::st_*); main loop and epilogue are those of the im2col-rows layer.
+template <bool kFQ, bool kRes, bool kQ8, int kGroups = 1, bool kRagged = false, bool kPair = false, bool kStem = false>
 __global__ void __launch_bounds__(kFQ ? kThreadsFq : 64 + kGroups * kEpiWarps * 32, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
@@ -412,6 +428,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const ConvGeom& gm = prm.gm;
     const int KC = prm.KC, BN = prm.BN, stages = prm.stages;
     static_assert(!kPair || (!kFQ && kGroups == 1), "the CTA-pair variant covers the plain main loop");
+    static_assert(!kStem || kFQ, "the fused stem is a producer mode of the fused-quantize kernel");
     const bool halo = !kFQ && !kPair && prm.halo != 0;
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
     const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = (kPair ? BN / 2 : BN) * KC,
@@ -433,9 +450,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // work units: tiles, round-robin over the CTAs — or, for the pair variant, 256-pixel pair tiles over the CTA pairs
-    const int total_tiles = kPair ? ((prm.m_tiles + 1) >> 1) * prm.n_tiles : prm.m_tiles * prm.n_tiles;
-    const int unit0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int unit_step = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    // (fused stem: every CTA takes a CONTIGUOUS run of tiles, so that consecutive tiles share quantized input rows)
+    const int all_tiles = kPair ? ((prm.m_tiles + 1) >> 1) * prm.n_tiles : prm.m_tiles * prm.n_tiles;
+    const int stem_run = kStem ? (all_tiles + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_tiles = kStem ? min(all_tiles, ((int)blockIdx.x + 1) * stem_run) : all_tiles;
+    const int unit0 = kStem ? (int)blockIdx.x * stem_run : (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+    const int unit_step = kStem ? 1 : (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
     const int kblocks = gm.R * gm.S * prm.cblocks;
 
     if (warp == 0 && lane == 0) {
@@ -519,7 +539,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int r = 0; r < gm.R; ++r)
                     for (int s = 0; s < gm.S; ++s)
                         for (int cb = 0; cb < prm.cblocks; ++cb) {
-                            mbar_wait<kFQ ? 200 : 0>(&empty[stage], phase ^ 1, prm.err_flag, 1);
+                            mbar_wait<(kFQ && !kStem) ? 200 : 0>(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
                             uint8_t* sb = sa + a_bytes;
                             if constexpr (kPair) {
@@ -564,7 +584,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t phase = 0, acc_phase = 0, hphase = 0;
         uint32_t stage_lo = base16;
         for (int tile = unit0; tile < total_tiles && pair_rank == 0; tile += unit_step) {   // (pair: the leader issues for both)
-            mbar_wait<kFQ ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
+            mbar_wait<(kFQ && !kStem) ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * prm.acc_stride);
             uint32_t accumulate = 0;
@@ -637,7 +657,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
             } else {
                 for (int kb = 0; kb < kblocks; ++kb) {
-                    mbar_wait<kFQ ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
+                    mbar_wait<(kFQ && !kStem) ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
                     tc_fence_after();
                     if (kPair) {
                         if (lane == 0) {
@@ -690,9 +710,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < kPrefetch; ++i) prefetch_next();
             int xs = 0;
             uint32_t xphase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = kStem ? unit0 : (int)blockIdx.x; tile < total_tiles; tile += kStem ? 1 : (int)gridDim.x) {
                 const int m_tile = tile / prm.n_tiles;
                 const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                if constexpr (kStem) {
+                    // the input rows of the tile's output rows, all channels: one box (rows outside the image: zeros)
+                    const int h0 = ((t * kBM) / g.Q) * g.stride - g.pad;
+                    mbar_wait(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
+                    mbar_expect_tx(&xfull[xs], (uint32_t)prm.st_patch_bytes);
+                    tma_load_4d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], 0, h0, 0, img);
+                    if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    continue;
+                }
                 for (int cb = 0; cb < prm.cblocks; ++cb) {
                     prefetch_next();
                     mbar_wait<200>(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
@@ -709,6 +738,110 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // layout the MMA reads.  A thread owns 4 consecutive pixels x 8 channels (8 conflict-free 16-byte loads),
         // quantizes them exactly like the standalone quantizer (quant_math.cuh) and stores four 8-byte channel vectors.
         const QuantParams qp = load_params(prm.q_scale, prm.q_zero, prm.q_qmin, prm.q_qmax);
+        if constexpr (kStem) {
+            // ---- fused stem: fp32 input rows -> quantized byte planes -> grouped im2col rows (the A k-blocks) ----
+            // The planes are a ring of st_ring input rows per channel (slot = (row + pad) mod st_ring): consecutive tiles of
+            // the CTA's run share all but ~2 of their input rows, so each row is quantized once per run, not once per tile
+            // (re-quantizing the 9-11 rows of every tile made the kernel instruction-bound: 720 us instead of 450).
+            const int qw = warp - (3 + kEpiWarps);          // 0..7
+            const int qt = qw * 32 + lane;                  // 0..255
+            uint32_t* plane32 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes + 2 * prm.wcls_smem);
+            const int Wq4 = prm.st_Wq >> 2, W4 = g.W >> 2, m4 = prm.st_margin >> 2;
+            const int ring = prm.st_ring, rmask = ring - 1;
+            const int PQs = g.P * g.Q;
+            auto qbar = [] { asm volatile("bar.sync 8, %0;" ::"n"(kFqWarps * 32) : "memory"); };
+            for (int i = qt; i < (prm.st_plane_bytes >> 2); i += kFqWarps * 32) plane32[i] = 0u;   // margins stay 0 for good
+            qbar();
+            const int row = qt & (kBM - 1), gh = qt >> 7;   // this thread's A row; its half of each k-block's 8 groups (warp-uniform)
+            const uint32_t swz = (uint32_t)((row >> 1) & 3);
+            const uint32_t plane_s = smem_u32(plane32);
+            const uint32_t cplane = (uint32_t)(ring * Wq4) * 4u;            // bytes between channel planes
+            // 16-byte chunk slots of this thread's A row (SWIZZLE_64B: chunk ^= (row >> 1) & 3), chunks 2*gh and 2*gh + 1
+            const uint32_t a_row = (uint32_t)(row * kFqKC), ch0 = ((uint32_t)(2 * gh) ^ swz) << 4, ch1 = ((uint32_t)(2 * gh + 1) ^ swz) << 4;
+            int xs = 0, stage = 0;
+            uint32_t xphase = 0, phase = 0;
+            int cur_img = -1, h_done = 0;                   // input rows [.., h_done) of image cur_img are in the ring
+            for (int tile = unit0; tile < total_tiles; ++tile) {
+                const int m_tile = prm.fd_ntiles.div(tile);
+                const int img = prm.fd_tpi.div(m_tile), t = m_tile - img * prm.tiles_per_img;
+                const int pq0 = t * kBM;
+                const int p_first = prm.fd_q.div(pq0);
+                const int p_last = prm.fd_q.div(min(pq0 + kBM, PQs) - 1);
+                const int h0 = p_first * g.stride - g.pad;
+                const int h_end = p_last * g.stride - g.pad + g.R;
+                if (img != cur_img) { cur_img = img; h_done = h0; }
+                const int h_new = max(h_done, h0), n_new = h_end - h_new;     // rows to quantize now
+                h_done = h_end;
+                mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
+                const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes);
+                // quantize: a warp takes whole (channel, row) lines, a lane 4 consecutive columns
+                if (n_new > 0) {
+                    int c = 0, rr = qw;
+                    while (true) {
+                        while (rr >= n_new && c < g.C) { rr -= n_new; ++c; }
+                        if (c >= g.C) break;
+                        const int ih = h_new + rr;
+                        const float* xl = xt + (c * prm.st_rows_box + (ih - h0)) * g.W;
+                        uint32_t* pl = plane32 + (c * ring + ((ih + g.pad) & rmask)) * Wq4 + m4;
+                        if ((unsigned)ih < (unsigned)g.H) {
+                            for (int j = lane; j < W4; j += 32) {
+                                const float4 v = lds4(xl + 4 * j);
+                                pl[j] = quant_word(v.x, v.y, v.z, v.w, qp);
+                            }
+                        } else {
+                            for (int j = lane; j < W4; j += 32) pl[j] = 0u;
+                        }
+                        rr += kFqWarps;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&xempty[xs]);     // this warp has read its part of the fp32 patch
+                if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                qbar();                                      // planes complete
+                // this thread's output pixel: window origin inside the planes
+                const int pq = min(pq0 + row, PQs - 1);
+                const int pi = prm.fd_q.div(pq), qi = pq - pi * g.Q;
+                const int col = qi * g.stride - g.pad + prm.st_margin;      // first byte of the 8-byte windows
+                const uint32_t wcol = plane_s + (uint32_t)(col & ~3);
+                const int sh = (col & 3) * 8;
+                const int slot0 = pi * g.stride;                            // ring slot of filter row 0 (before the mask)
+                uint32_t rb[7];                                             // shared address of the window in filter row rf, channel 0
+#pragma unroll
+                for (int rf = 0; rf < 7; ++rf) rb[rf] = wcol + (uint32_t)(((slot0 + rf) & rmask) * Wq4) * 4u;
+                // groups of this thread in k-block kb: gi = 8 * kb + 4 * gh + j  ->  channel gi / 7, filter row gi % 7 (R == 7)
+                auto build = [&](auto gh_tag) {
+                    constexpr int GH = decltype(gh_tag)::value;
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        if (kb < prm.cblocks) {
+                            mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
+                            const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes + a_row;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int gi = kb * 8 + GH * 4 + j;
+                                const int c = gi / 7, rf = gi % 7;
+                                if (c < g.C) {                              // (bytes past the last group meet zero weights)
+                                    const uint32_t a = rb[rf] + (uint32_t)c * cplane;
+                                    uint32_t w0, w1, w2;
+                                    asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
+                                                 : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(a));
+                                    const uint32_t dst = sa + (j < 2 ? ch0 : ch1) + (uint32_t)((j & 1) << 3);
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(__funnelshift_r(w0, w1, sh)),
+                                                 "r"(__funnelshift_r(w1, w2, sh)) : "memory");
+                                }
+                            }
+                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&full[stage]);
+                            if (++stage == stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                };
+                if (gh == 0) build(std::integral_constant<int, 0>{});
+                else build(std::integral_constant<int, 1>{});
+                qbar();                                      // new rows may replace ring slots the slowest warp still reads
+            }
+        } else {
         // All quantizer warps work on the same k-block (every barrier sees every phase: no parity aliasing):
         // warp pw owns channels [8*pw, 8*pw + 8) of the 64-channel k-block for all 128 pixels.
         const int pw = warp - (3 + kEpiWarps);
@@ -765,6 +898,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (++stage == stages) { stage = 0; phase ^= 1; }
             }
         }
+        }   // !kStem
     } else {
         // ===================== epilogue =====================
         const int grp = kGroups > 1 ? (warp - 2) >> 3 : 0;   // epilogue group: tiles grp, grp + kGroups, ... of this CTA
@@ -911,10 +1045,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const float* wrow = be;
             if (use_cls) {
                 int rc = 0, cx = 0;
-                for (int i = 0; i < prm.n_rcls; ++i)
-                    if (prm.rcls[i][0] == pw.r0 && prm.rcls[i][1] == pw.r1) rc = i;
-                for (int i = 0; i < prm.n_ccls; ++i)
-                    if (prm.ccls[i][0] == pw.s0 && prm.ccls[i][1] == pw.s1) cx = i;
+                if (prm.cls_fast) {   // classes in order of first occurrence: head rows, the full window, tail rows (host-verified)
+                    rc = min(p, prm.cls_head_r) + max(0, p - prm.cls_tail_r + 1);
+                    cx = min(q, prm.cls_head_c) + max(0, q - prm.cls_tail_c + 1);
+                } else {
+                    for (int i = 0; i < prm.n_rcls; ++i)
+                        if (prm.rcls[i][0] == pw.r0 && prm.rcls[i][1] == pw.r1) rc = i;
+                    for (int i = 0; i < prm.n_ccls; ++i)
+                        if (prm.ccls[i][0] == pw.s0 && prm.ccls[i][1] == pw.s1) cx = i;
+                }
                 wrow = wcls + (rc * prm.n_ccls + cx) * BN;
             }
             const bool uniform_ok = use_cls || warp_interior;
@@ -922,7 +1061,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int i11 = pw.r1 * s1 + pw.s1, i01 = pw.r0 * s1 + pw.s1, i10 = pw.r1 * s1 + pw.s0, i00 = pw.r0 * s1 + pw.s0;
             const int64_t o_base = ((int64_t)img * g.K + k_base) * PQ + pq;
 
-            if (kFQ) mbar_wait_sleepy<500>(&acc_full[buf], acc_phase, prm.err_flag, 4);
+            if (kFQ && !kStem) mbar_wait_sleepy<500>(&acc_full[buf], acc_phase, prm.err_flag, 4);   // (stem tiles are ~1 us: no sleeps on its critical path)
             else mbar_wait(&acc_full[buf], acc_phase, prm.err_flag, 4);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * prm.acc_stride + half * cols);
@@ -1247,6 +1386,34 @@ bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
            g.C % 64 == 0 && reinterpret_cast<uintptr_t>(x) % 16 == 0;
 }
 
+// Fused stem: a few-channel layer whose grouped im2col rows (8 bytes per (channel, filter row)) the quantizer warps can
+// build in shared memory: the fp32 rows of one tile fit a ring slot, the byte planes fit their buffer, one channel tile.
+namespace {
+struct StemPlan { int rows_box, Wq, margin, patch_bytes, plane_bytes, ring; };
+bool stem_plan(const ConvGeom& g, StemPlan* out) {
+    if (g.groups != 1 || g.C > 4 || g.R != 7 || !im2col_grouped(g.C, g.R, g.S)) return false;   // (the row builder is unrolled for R == 7)
+    if (im2col8_row_bytes(g.C, g.R) % kFqKC != 0 || g.K > 256 || g.W % 4 != 0 || g.W > 256 || g.Q < 1) return false;
+    StemPlan sp;
+    const int rows_out = (kBM - 2) / g.Q + 2;              // output rows a 128-pixel tile can touch
+    sp.rows_box = (rows_out - 1) * g.stride + g.R;
+    sp.margin = (g.pad + 3) & ~3;
+    const int need = std::max(sp.margin + g.W + g.pad, (g.Q - 1) * g.stride - g.pad + sp.margin + 12);
+    sp.Wq = (need + 3) & ~3;
+    sp.patch_bytes = g.C * sp.rows_box * g.W * 4;
+    sp.ring = 8;
+    while (sp.ring < sp.rows_box) sp.ring <<= 1;           // ring of input rows per channel plane (a power of two)
+    sp.plane_bytes = (g.C * sp.ring * sp.Wq + 15) & ~15;
+    if (im2col8_row_bytes(g.C, g.R) > 4 * kFqKC) return false;
+    if (sp.rows_box > 256 || sp.patch_bytes > kFqKC * kBM * 4 || sp.plane_bytes > 16 * 1024) return false;
+    if (out) *out = sp;
+    return true;
+}
+}  // namespace
+bool umma_stem_supported(const ConvGeom& g, const float* x) {
+    return umma_supported(g) && stem_plan(g, nullptr) && reinterpret_cast<uintptr_t>(x) % 16 == 0 &&
+           (int64_t)g.N * g.P * g.Q < (1ll << 31);
+}
+
 // Measured on B200 (profiles/README.md): the in-kernel quantizer (8 warps) sustains ~3.5 TB/s of fp32 input, the
 // standalone quantizer ~5.5 TB/s.  Fusing wins when the layer is output-heavy and large: one 64-channel k-block per
 // tile (C == 64) on feature maps of at least 28x28; everything else keeps the two-kernel path.
@@ -1270,7 +1437,14 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
                "conv_umma: layer not eligible for the halo variant");
     QB_REQUIRE(!(fq && (ep.residual || ep.q8_out)), QB200_EINVAL, "conv_umma: the fused-quantize kernel has no residual / hand-off tail");
-    if (fq) {
+    const bool stem = fq && gemm_rows > 0;   // fused stem: x_fused is the fp32 input of an im2col-rows layer
+    StemPlan sp = {0, 0, 0, 0, 0, 0};
+    if (stem) {
+        QB_REQUIRE(umma_stem_supported(g, x_fused) && stem_plan(g, &sp) && gemm_rows == im2col8_row_bytes(g.C, g.R) && aq_fused &&
+                       aq_fused->qmin && aq_fused->qmax,
+                   QB200_EINVAL, "conv_umma: layer not eligible for the fused stem kernel");
+        qa = reinterpret_cast<const uint8_t*>(x_fused);
+    } else if (fq) {
         QB_REQUIRE(umma_fused_quant_supported(g, x_fused) && gemm_rows == 0 && aq_fused && aq_fused->qmin && aq_fused->qmax,
                    QB200_EINVAL, "conv_umma: layer not eligible for the fused-quantize kernel");
         qa = reinterpret_cast<const uint8_t*>(x_fused);  // only used for alignment checks below
@@ -1312,6 +1486,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.halo_bytes = (int)align_up_sz((size_t)prm.halo_rows * prm.KC, 1024);
     prm.h_stages = 0;
     prm.x_stages = 0;
+    prm.st_rows_box = sp.rows_box;
+    prm.st_Wq = sp.Wq;
+    prm.st_margin = sp.margin;
+    prm.st_patch_bytes = sp.patch_bytes;
+    prm.st_plane_bytes = sp.plane_bytes;
+    prm.st_ring = sp.ring;
     prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
     prm.m_tiles = (fq || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
@@ -1338,6 +1518,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     } else {
         while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
     }
+    if (stem) BN = g.K > 128 ? 256 : (g.K > 64 ? 128 : 64);   // one channel tile: the rows are built once per pixel tile
     prm.BN = BN;
     // more tiles in flight where they are small: the MMA of tile i+3 need not wait for the epilogue of tile i+1
     prm.n_acc = BN <= 128 ? 4 : 2;
@@ -1362,6 +1543,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
     prm.wcls_smem = 0;
     prm.n_rcls = prm.n_ccls = 0;
+    prm.cls_fast = prm.cls_head_r = prm.cls_tail_r = prm.cls_head_c = prm.cls_tail_c = 0;
     if (g.R * g.S > 1) {
         auto classes = [&](int n_out, int in_dim, int taps, uint8_t (*dst)[2]) {
             int n = 0;
@@ -1383,6 +1565,21 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             prm.n_rcls = nr;
             prm.n_ccls = nc;
             prm.wcls_smem = nr * nc * BN * 4;
+            // closed form of "which class is output row / column o": verified here against the enumeration
+            auto closed = [&](int n_out, int in_dim, int taps, const uint8_t (*cls)[2], int n_cls, int* head, int* tail) {
+                *head = (g.pad + g.stride - 1) / g.stride;                        // rows whose window starts above the image
+                const int t = in_dim - taps + g.pad;
+                *tail = t >= 0 ? t / g.stride + 1 : 0;                            // first row whose window ends below it
+                for (int o = 0; o < n_out; ++o) {
+                    const int h0 = o * g.stride - g.pad;
+                    const int lo = h0 < 0 ? -h0 : 0, hi = taps < in_dim - h0 ? taps : in_dim - h0;
+                    const int c = std::min(o, *head) + std::max(0, o - *tail + 1);
+                    if (c < 0 || c >= n_cls || cls[c][0] != lo || cls[c][1] != hi) return false;
+                }
+                return true;
+            };
+            prm.cls_fast = closed(g.P, g.H, g.R, prm.rcls, nr, &prm.cls_head_r, &prm.cls_tail_r) &&
+                           closed(g.Q, g.W, g.S, prm.ccls, nc, &prm.cls_head_c, &prm.cls_tail_c);
         }
     }
     // residual tail: stream the identity through per-warp cp.async rings when 16-byte pieces line up (4 pixels of one
@@ -1392,12 +1589,13 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         reinterpret_cast<uintptr_t>(ep.residual) % 16 == 0 && prm.M < (1ll << 31) &&
         kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq)
         prm.res_async = 1;
-    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0);
+    const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0) + (stem ? (size_t)sp.plane_bytes : 0);
     size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail;
     const size_t xb = (size_t)kFqKC * kBM * 4;
     if (fq) {
         // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
-        int xs = kMaxXStages;
+        // (fused stem: a slot holds the rows of a whole tile, four slots cover the load latency; the rest goes to A/B stages)
+        int xs = stem ? 4 : kMaxXStages;
         while (xs > 3 && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
@@ -1416,6 +1614,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     int stages = (int)(ring_budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
+    QB_REQUIRE(!stem || prm.n_tiles == 1, QB200_EUNSUPPORTED, "conv_umma: the fused stem needs a single channel tile");
     prm.stages = stages;
     prm.layout = prm.KC == 128 ? 2u : (prm.KC == 64 ? 4u : 6u);  // SWIZZLE_128B / 64B / 32B
     prm.sbo16 = (uint32_t)(8 * prm.KC) >> 4;
@@ -1507,6 +1706,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
+        QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<true, false, false, 1, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, false, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         if (cur_dev >= 0 && cur_dev < 64) smem_set_mask.fetch_or(1ull << cur_dev, std::memory_order_release);
@@ -1523,7 +1723,19 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_LAUNCH_CHECK();
         return 0;
     }
-    if (fq) {
+    if (stem) {
+        // fp32 input as (W, H, C, N); box = whole rows x st_rows_box rows x all channels of one image, zero fill outside
+        cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.C, (cuuint64_t)g.N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)g.C * g.H * g.W * 4};
+        cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)sp.rows_box, (cuuint32_t)g.C, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = api.tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x_fused), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled(fp32 stem rows) failed with CUresult %d", (int)r);
+        QB_CUDA(launch_pdl(conv_umma_kernel<true, false, false, 1, false, false, true>, dim3(grid), dim3(kThreadsFq), smem, st, tmap_a,
+                           tmap_b, prm, out));
+    } else if (fq) {
         // fp32 input as (pixels, channels, images); box = 128 pixels x 64 channels, no swizzle, zero fill past H*W
         cuuint64_t dims[3] = {(cuuint64_t)g.H * g.W, (cuuint64_t)g.C, (cuuint64_t)g.N};
         cuuint64_t strides[2] = {(cuuint64_t)g.H * g.W * 4, (cuuint64_t)g.C * g.H * g.W * 4};

@@ -410,3 +410,33 @@ def test_cta_pair_deep_reductions(cfg):
     assert np.array_equal(acc_p.cpu().numpy(), acc_ref)
     assert torch.equal(acc_p, acc_1) and torch.equal(out_p, out_1)
     assert_close_1e3(out_p.cpu().numpy(), out_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused stem (round 2): few-channel 7x7-type layers — the grouped im2col rows are built in shared memory from the fp32
+# input inside the tensor-core kernel instead of being written to and read back from HBM
+# ---------------------------------------------------------------------------------------------------
+STEM_CASES = [
+    # N, C, H, W, K, R, stride, pad, relu_input
+    (3, 3, 224, 224, 64, 7, 2, 3, False),    # the ImageNet ResNet stem: 98 tiles per image, tiles span 2-3 output rows
+    (2, 3, 60, 60, 64, 7, 2, 3, False),      # 30x30 outputs: a tile spans 5-6 output rows, ragged last tile (900 = 7*128 + 4)
+    (2, 1, 64, 48, 32, 7, 1, 3, True),       # one channel (64-byte rows, one k-block), stride 1, zero point 0
+    (1, 2, 36, 40, 128, 7, 2, 3, False),     # two channels (128-byte rows), 128 output channels
+    (5, 3, 32, 32, 256, 7, 1, 2, False),     # pad 2 (margin 4 > pad), asymmetric borders, K = 256
+    (1, 3, 20, 16, 64, 7, 2, 3, False),      # a single ragged tile per image (10 x 8 outputs)
+]
+
+
+@pytest.mark.parametrize("cfg", STEM_CASES)
+def test_fused_stem_rows_built_in_shared_memory(cfg):
+    N, C, H, W, K, R, stride, pad, relu = cfg
+    c = random_conv_case(sum(cfg[:8]) + 11, N, C, H, W, K, R, stride, pad, relu=relu)
+    L = capi.lib()
+    x = torch.from_numpy(c["x"]).cuda()
+    assert L.qb200_conv_is_single_kernel(ctypes.byref(c["shape"]), x.data_ptr()) == 1
+    acc_s, out_s = run_case(c, capi.ALGO_AUTO)            # the product's choice: fused stem
+    acc_2, out_2 = run_case(c, ALGOS["umma2k"])           # quantizer writes the rows, the conv reads them back
+    _, acc_ref, out_ref = oracle_case(c)
+    assert np.array_equal(acc_s.cpu().numpy(), acc_ref)
+    assert torch.equal(acc_s, acc_2) and torch.equal(out_s, out_2)
+    assert_close_1e3(out_s.cpu().numpy(), out_ref)
