@@ -46,7 +46,8 @@ constexpr int kThreadsFq = kThreads + 32 + kFqWarps * 32;  // + one TMA warp for
 constexpr int kMaxXStages = 6;      // fp32 staging ring of the fused-quantize variant (3..6 slots, what fits) / halo ring (<= 3)
 constexpr int kFqKC = 64;           // its k-block: 64 channels (a 32 KB fp32 tile, an 8 KB u8 A tile)
 constexpr int kConstFloats = 3 * 256;  // per-tile channel constants: scale, interior bias, raw bias
-constexpr int kBarBytes = 576;                           // mbarriers + TMEM slot
+constexpr int kMaxBoxes = 16;        // fused stem: ring of fp32 row boxes (own barriers behind the common ones)
+constexpr int kBarBytes = 576 + 2 * kMaxBoxes * 8;       // mbarriers + TMEM slot (+ the box barriers)
 constexpr int kTailBytes = kBarBytes + 2 * kConstFloats * 4;  // barriers + two constant buffers
 constexpr int kMaxWclsBytes = 16 * 1024;                 // one buffer of per-window-class channel sums (layers with R*S > 1)
 constexpr int kMaxCls = 16;                              // distinct row (and column) windows supported by the class table
@@ -120,7 +121,7 @@ struct UmmaParams {
     // shared memory from the fp32 input — the rows never exist in HBM.  Per tile ONE 4-D TMA box [C][st_rows_box][W] of
     // fp32 input rows (rows outside the image zero-filled) -> quantized byte planes [C][st_rows_box][st_Wq] (input column
     // iw at byte st_margin + iw; margins stay 0 = the reference's zero padding) -> 8-byte windows of the planes.
-    int st_rows_box, st_Wq, st_margin, st_patch_bytes, st_plane_bytes, st_ring;
+    int st_rows_box, st_Wq, st_margin, st_box_bytes, st_box_pitch, st_plane_bytes, st_ring, st_dbg;   // (pitch: boxes 128-byte aligned in the slot)
     const float* x;
     const float* q_scale;
     const float* q_zero;
@@ -383,7 +384,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void epi_barrier(int group) { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kEpiWarps * 32) : "memory"); }
+template <int kThreadsInGroup>
+__device__ __forceinline__ void epi_barrier(int group) { asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kThreadsInGroup) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (tcgen05): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46 | layout <<61
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(kFQ ? kThreadsFq : 64 + kGroups * kEpiWarps * 
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const UmmaParams prm, void* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);   // (stage ring base)
 
     const ConvGeom& g = prm.g;
     const ConvGeom& gm = prm.gm;
@@ -432,9 +434,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool halo = !kFQ && !kPair && prm.halo != 0;
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
     const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = (kPair ? BN / 2 : BN) * KC,
-                   stage_bytes = halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes;
+                   stage_bytes = kStem ? a_bytes : (halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes);
+    // fused stem: the whole weight matrix (cblocks tiles) stays resident in front of the ring; a stage is an A tile only
+    uint8_t* const bres = smem;
+    if constexpr (kStem) smem += (size_t)prm.cblocks * b_bytes;
     uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [x_stages][KC][128] fp32
-    const uint32_t x_bytes = kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u);  // ring slot size
+    const uint32_t x_bytes = kStem ? (uint32_t)prm.st_box_pitch
+                                   : (kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u));  // ring slot size
     const int x_slots = kFQ ? prm.x_stages : (halo ? prm.h_stages : 0);       // fp32 tiles (kFQ) or u8 halo tiles (halo)
     uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)x_slots * x_bytes);
     uint64_t* full = bars;                     // [stages]
@@ -444,6 +450,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint64_t* xfull = bars + 2 * kMaxStages + 2 * kMaxAcc;  // [kMaxXStages]
     uint64_t* xempty = xfull + kMaxXStages;          // [kMaxXStages]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty + kMaxXStages);
+    uint64_t* bfull = bars + 72;               // [kMaxBoxes] fused stem: one fp32 row box each (byte offset 576)
+    uint64_t* bempty = bfull + kMaxBoxes;      // [kMaxBoxes]
     float* consts = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kBarBytes);  // [2][3][256]
     float* wcls_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes);  // [2][n_cls][BN]
 
@@ -462,16 +470,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int i = 0; i < stages; ++i) {
-            mbar_init(&full[i], kFQ ? 1 + kFqWarps : 1);  // TMA expect_tx arrival (+ one arrival per quantizer warp)
+            mbar_init(&full[i], kStem ? kFqWarps : (kFQ ? 1 + kFqWarps : 1));  // TMA expect_tx arrival (+ one arrival per quantizer warp; stem: the warps only)
             mbar_init(&empty[i], 1);
         }
         for (int i = 0; i < kMaxAcc; ++i) {
             mbar_init(&acc_full[i], 1);
-            mbar_init(&acc_empty[i], kPair ? 2 * kEpiWarps : kEpiWarps);   // pair: the epilogue warps of both CTAs
+            mbar_init(&acc_empty[i], kPair ? 2 * kEpiWarps : (kStem ? 4 : kEpiWarps));   // pair: the epilogue warps of both CTAs; stem: groups of four warps
         }
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&xfull[i], 1);
             mbar_init(&xempty[i], kFQ ? kFqWarps : 1);
+        }
+        if constexpr (kStem) {
+            for (int i = 0; i < kMaxBoxes; ++i) {
+                mbar_init(&bfull[i], 1);
+                mbar_init(&bempty[i], kFqWarps);
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -527,7 +541,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
             }
-            for (int tile = unit0; !halo && tile < total_tiles; tile += unit_step) {
+            if constexpr (kStem) {   // the weights: once per CTA, all k-blocks, one barrier (the spare slot of the x ring's)
+                uint64_t* wfull = &xfull[kMaxXStages - 1];
+                mbar_expect_tx(wfull, (uint32_t)prm.cblocks * b_bytes);
+                for (int cb = 0; cb < prm.cblocks; ++cb) tma_load_2d(bres + (size_t)cb * b_bytes, &tmap_b, wfull, cb * KC, 0);
+            }
+            for (int tile = unit0; !kStem && !halo && tile < total_tiles; tile += unit_step) {
                 const int n_tile = tile % prm.n_tiles;
                 // pair: this CTA loads the rows of m-tile 2 * (pair tile) + rank; an odd tail re-loads the last tile
                 const int m_tile = kPair ? min(2 * (tile / prm.n_tiles) + (int)pair_rank, prm.m_tiles - 1) : tile / prm.n_tiles;
@@ -583,6 +602,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int stage = 0, buf = 0, hs = 0;
         uint32_t phase = 0, acc_phase = 0, hphase = 0;
         uint32_t stage_lo = base16;
+        if constexpr (kStem) mbar_wait(&xfull[kMaxXStages - 1], 0, prm.err_flag, 3);   // resident weights have landed
+        const uint32_t bres16 = smem_u32(bres) >> 4;
         for (int tile = unit0; tile < total_tiles && pair_rank == 0; tile += unit_step) {   // (pair: the leader issues for both)
             mbar_wait<(kFQ && !kStem) ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
@@ -667,7 +688,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                             umma_commit_pair(&empty[stage]);   // the slot is reusable in BOTH CTAs
                         }
                     } else if (lane == 0) {
-                        const uint32_t a0 = stage_lo | lo_flag, b0 = (stage_lo + a16) | lo_flag;
+                        const uint32_t a0 = stage_lo | lo_flag,
+                                       b0 = (kStem ? bres16 + (uint32_t)kb * (b_bytes >> 4) : stage_lo + a16) | lo_flag;
                         if (n_mma == 4) {          // KC = 128
                             umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
                             umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);
@@ -710,16 +732,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < kPrefetch; ++i) prefetch_next();
             int xs = 0;
             uint32_t xphase = 0;
+            int st_img = -1, st_done = 0;
             for (int tile = kStem ? unit0 : (int)blockIdx.x; tile < total_tiles; tile += kStem ? 1 : (int)gridDim.x) {
                 const int m_tile = tile / prm.n_tiles;
                 const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
                 if constexpr (kStem) {
-                    // the input rows of the tile's output rows, all channels: one box (rows outside the image: zeros)
-                    const int h0 = ((t * kBM) / g.Q) * g.stride - g.pad;
-                    mbar_wait(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
-                    mbar_expect_tx(&xfull[xs], (uint32_t)prm.st_patch_bytes);
-                    tma_load_4d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], 0, h0, 0, img);
-                    if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    // the input rows this tile adds to the ring (same bookkeeping as the quantizer warps), as boxes of
+                    // `stride` rows x all channels; rows outside the image arrive as zeros
+                    const int pq0 = t * kBM;
+                    const int p_first = prm.fd_q.div(pq0), p_last = prm.fd_q.div(min(pq0 + kBM, g.P * g.Q) - 1);
+                    const int h0 = p_first * g.stride - g.pad, h_end = p_last * g.stride - g.pad + g.R;
+                    if (img != st_img) { st_img = img; st_done = h0; }
+                    const int h_new = max(st_done, h0), n_new = h_end - h_new;
+                    st_done = h_end;
+                    if (n_new <= 0) continue;
+                    const int nb = (n_new + g.stride - 1) / g.stride;
+                    for (int b = 0; b < nb; ++b) {       // one ring slot and one barrier pair per box
+                        mbar_wait(&bempty[xs], xphase ^ 1, prm.err_flag, 6);
+                        mbar_expect_tx(&bfull[xs], (uint32_t)prm.st_box_bytes);
+                        tma_load_4d(xring + (size_t)xs * x_bytes, &tmap_a, &bfull[xs], 0, h_new + b * g.stride, 0, img);
+                        if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    }
                     continue;
                 }
                 for (int cb = 0; cb < prm.cblocks; ++cb) {
@@ -772,31 +805,32 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 if (img != cur_img) { cur_img = img; h_done = h0; }
                 const int h_new = max(h_done, h0), n_new = h_end - h_new;     // rows to quantize now
                 h_done = h_end;
-                mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
-                const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes);
-                // quantize: a warp takes whole (channel, row) lines, a lane 4 consecutive columns
-                if (n_new > 0) {
-                    int c = 0, rr = qw;
-                    while (true) {
-                        while (rr >= n_new && c < g.C) { rr -= n_new; ++c; }
-                        if (c >= g.C) break;
-                        const int ih = h_new + rr;
-                        const float* xl = xt + (c * prm.st_rows_box + (ih - h0)) * g.W;
-                        uint32_t* pl = plane32 + (c * ring + ((ih + g.pad) & rmask)) * Wq4 + m4;
-                        if ((unsigned)ih < (unsigned)g.H) {
-                            for (int j = lane; j < W4; j += 32) {
-                                const float4 v = lds4(xl + 4 * j);
-                                pl[j] = quant_word(v.x, v.y, v.z, v.w, qp);
+                // quantize the new rows, box by box (`stride` rows x all channels each): a warp takes whole (channel, row)
+                // lines of the box, a lane 4 consecutive columns
+                for (int b0 = 0; b0 < n_new; b0 += g.stride) {
+                    mbar_wait(&bfull[xs], xphase, prm.err_flag, 7);
+                    const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes);
+                    if (!(prm.st_dbg & 1)) {
+                        for (int ln = qw; ln < g.C * g.stride; ln += kFqWarps) {
+                            const int c = g.stride == 1 ? ln : (g.stride == 2 ? ln >> 1 : ln / g.stride), rin = ln - c * g.stride;
+                            const int ih = h_new + b0 + rin;
+                            if (ih >= h_end) continue;                         // (a box may reach past the tile's last row)
+                            const float* xl = xt + ln * g.W;
+                            uint32_t* pl = plane32 + (c * ring + ((ih + g.pad) & rmask)) * Wq4 + m4;
+                            if ((unsigned)ih < (unsigned)g.H) {
+                                for (int j = lane; j < W4; j += 32) {
+                                    const float4 v = lds4(xl + 4 * j);
+                                    pl[j] = quant_word(v.x, v.y, v.z, v.w, qp);
+                                }
+                            } else {
+                                for (int j = lane; j < W4; j += 32) pl[j] = 0u;
                             }
-                        } else {
-                            for (int j = lane; j < W4; j += 32) pl[j] = 0u;
                         }
-                        rr += kFqWarps;
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&bempty[xs]);     // this warp has read its part of the box
+                    if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&xempty[xs]);     // this warp has read its part of the fp32 patch
-                if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
                 qbar();                                      // planes complete
                 // this thread's output pixel: window origin inside the planes
                 const int pq = min(pq0 + row, PQs - 1);
@@ -815,12 +849,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     for (int kb = 0; kb < 4; ++kb) {
                         if (kb < prm.cblocks) {
                             mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
-                            const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes + a_row;
+                            const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes + a_row;   // (smem = ring base, past the resident weights)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int gi = kb * 8 + GH * 4 + j;
                                 const int c = gi / 7, rf = gi % 7;
-                                if (c < g.C) {                              // (bytes past the last group meet zero weights)
+                                if (c < g.C && !(prm.st_dbg & 2)) {                              // (bytes past the last group meet zero weights)
                                     const uint32_t a = rb[rf] + (uint32_t)c * cplane;
                                     uint32_t w0, w1, w2;
                                     asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
@@ -901,11 +935,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }   // !kStem
     } else {
         // ===================== epilogue =====================
-        const int grp = kGroups > 1 ? (warp - 2) >> 3 : 0;   // epilogue group: tiles grp, grp + kGroups, ... of this CTA
-        const int e = (warp - 2) & 7;
+        // fused stem: the eight warps form TWO groups of four (one warp per lane quadrant, all columns) on alternate tiles —
+        // with 64-channel tiles the per-tile latency chain of the epilogue (address set-up, waits), not its instruction
+        // count, bounded the kernel: ~2200 cycles per tile with every store and FMA removed
+        constexpr int kGW = kStem ? 4 : kEpiWarps;           // warps per epilogue group
+        constexpr int kNG = kStem ? 2 : kGroups;             // groups
+        const int grp = kStem ? (warp - 2) >> 2 : (kGroups > 1 ? (warp - 2) >> 3 : 0);   // epilogue group: tiles grp, grp + kNG, ... of this CTA
+        const int e = (warp - 2) & (kGW - 1);
         const int quad = warp & 3;   // TMEM lane quadrant this warp may read
-        const int half = e >> 2;     // which half of the tile's columns
-        const int et = (threadIdx.x - 64) & (kEpiWarps * 32 - 1);   // thread index inside the group
+        const int half = kStem ? 0 : e >> 2;     // which half of the tile's columns
+        const int et = (threadIdx.x - 64) & (kGW * 32 - 1);   // thread index inside the group
         const int row = quad * 32 + lane;
         const int PQ = g.P * g.Q;
         const EpilogueParams& ep = prm.ep;
@@ -918,7 +957,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // (only the branch-free quantizer applies xlo; quant_word_exact — ranges outside a byte — keeps the explicit ReLU)
         const bool relu_folded = kQ8 && !kRes && ep.q8_out != nullptr && !ep.store_f32 && ep.relu != 0 && q8p.byte_clamp != 0;
         if (relu_folded) q8p.xlo = fmaxf(q8p.xlo, 0.f);
-        const int cols = BN >> 1;    // columns per warp: 32, 64 or 128
+        const int cols = kStem ? BN : BN >> 1;    // columns per warp: 32, 64 or 128 (stem: the whole tile)
         // ---- residual stream (fused tail) ----
         // The identity tensor is the largest read of a residual layer and a warp that loads one 32-channel chunk at a
         // time keeps too few bytes in flight for HBM latency (ncu: 40 % of the epilogue's samples waited on those
@@ -965,7 +1004,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int iter = 0;
         const uint32_t acc_empty_lead = kPair ? mapa_u32(smem_u32(&acc_empty[0]), 0) : 0u;   // the leader's barriers
         for (int tile = unit0 + grp * unit_step, it = grp; tile < total_tiles;
-             tile += kGroups * unit_step, it += kGroups, ++iter) {
+             tile += kNG * unit_step, it += kNG, ++iter) {
             const int buf = it & (prm.n_acc - 1);                       // the MMA warp fills the buffers in tile order
             const uint32_t acc_phase = (uint32_t)(it >> acc_shift) & 1u;
             const int u_tile = prm.fd_ntiles.div(tile);                 // m-tile, or pair of m-tiles
@@ -983,7 +1022,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (iter == 0 || prm.n_tiles > 1) {
                 if (use_cls) {
                     const int s1c = g.S + 1;
-                    for (int i = et; i < prm.n_rcls * prm.n_ccls * BN; i += kEpiWarps * 32) {
+                    for (int i = et; i < prm.n_rcls * prm.n_ccls * BN; i += kGW * 32) {
                         const int cls = i / BN, kk = i - cls * BN;
                         float val = 0.f;
                         if (k_base + kk < g.K) {
@@ -996,19 +1035,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         wcls[i] = val;
                     }
                 }
-                if (et < BN) {
-                    const int k = k_base + et;
+                for (int ek = et; ek < BN; ek += kGW * 32) {
+                    const int k = k_base + ek;
                     float scale = 0.f, bias = 0.f, beff = 0.f;  // beff: sum of all taps' weights (interior window), as float
                     if (k < g.K) {
                         scale = __fmul_rn(es.s_a, __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k)));
                         bias = ep.bias ? __ldg(ep.bias + k) : 0.f;
                         if (es.z_a != 0.f) beff = (float)__ldg(ep.wpre + (int64_t)(k + 1) * (g.R + 1) * (g.S + 1) - 1);
                     }
-                    sc[et] = scale;
-                    be[et] = beff;
-                    br[et] = bias;
+                    sc[ek] = scale;
+                    be[ek] = beff;
+                    br[ek] = bias;
                 }
-                epi_barrier(grp);
+                epi_barrier<kGW * 32>(grp);
             }
             bool row_ok;
             int img, pq;
@@ -1161,6 +1200,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         continue;
                     }
                 }
+                if constexpr (kStem) { if (prm.st_dbg & 4) continue; }
                 if (!acc_out && full_c && uniform_ok) {
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
@@ -1389,7 +1429,7 @@ bool umma_fused_quant_supported(const ConvGeom& g, const float* x) {
 // Fused stem: a few-channel layer whose grouped im2col rows (8 bytes per (channel, filter row)) the quantizer warps can
 // build in shared memory: the fp32 rows of one tile fit a ring slot, the byte planes fit their buffer, one channel tile.
 namespace {
-struct StemPlan { int rows_box, Wq, margin, patch_bytes, plane_bytes, ring; };
+struct StemPlan { int rows_box, Wq, margin, box_bytes, plane_bytes, ring; };
 bool stem_plan(const ConvGeom& g, StemPlan* out) {
     if (g.groups != 1 || g.C > 4 || g.R != 7 || !im2col_grouped(g.C, g.R, g.S)) return false;   // (the row builder is unrolled for R == 7)
     if (im2col8_row_bytes(g.C, g.R) % kFqKC != 0 || g.K > 256 || g.W % 4 != 0 || g.W > 256 || g.Q < 1) return false;
@@ -1399,12 +1439,12 @@ bool stem_plan(const ConvGeom& g, StemPlan* out) {
     sp.margin = (g.pad + 3) & ~3;
     const int need = std::max(sp.margin + g.W + g.pad, (g.Q - 1) * g.stride - g.pad + sp.margin + 12);
     sp.Wq = (need + 3) & ~3;
-    sp.patch_bytes = g.C * sp.rows_box * g.W * 4;
+    sp.box_bytes = g.C * g.stride * g.W * 4;               // one TMA box: `stride` input rows of every channel
     sp.ring = 8;
     while (sp.ring < sp.rows_box) sp.ring <<= 1;           // ring of input rows per channel plane (a power of two)
     sp.plane_bytes = (g.C * sp.ring * sp.Wq + 15) & ~15;
     if (im2col8_row_bytes(g.C, g.R) > 4 * kFqKC) return false;
-    if (sp.rows_box > 256 || sp.patch_bytes > kFqKC * kBM * 4 || sp.plane_bytes > 16 * 1024) return false;
+    if (sp.rows_box > 256 || sp.box_bytes > 24 * 1024 || sp.plane_bytes > 16 * 1024) return false;
     if (out) *out = sp;
     return true;
 }
@@ -1489,9 +1529,11 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.st_rows_box = sp.rows_box;
     prm.st_Wq = sp.Wq;
     prm.st_margin = sp.margin;
-    prm.st_patch_bytes = sp.patch_bytes;
+    prm.st_box_bytes = sp.box_bytes;
+    prm.st_box_pitch = (sp.box_bytes + 127) & ~127;
     prm.st_plane_bytes = sp.plane_bytes;
     prm.st_ring = sp.ring;
+    { const char* e = getenv("QB200_STEM_DBG"); prm.st_dbg = e ? atoi(e) : 0; }
     prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
     prm.m_tiles = (fq || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
@@ -1539,7 +1581,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
         else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
     }
-    const size_t stage_bytes = halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC;
+    const size_t stage_bytes = stem ? (size_t)kBM * prm.KC
+                                    : (halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC);
+    const size_t b_res = stem ? (size_t)prm.cblocks * BN * prm.KC : 0;   // fused stem: the weights stay resident, stages hold A only
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
     prm.wcls_smem = 0;
     prm.n_rcls = prm.n_ccls = 0;
@@ -1590,12 +1634,13 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq)
         prm.res_async = 1;
     const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0) + (stem ? (size_t)sp.plane_bytes : 0);
-    size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail;
-    const size_t xb = (size_t)kFqKC * kBM * 4;
+    size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail - b_res;
+    // ring slot of the fp32 input: a [64 channels][128 pixels] tile, or (fused stem) one box of `stride` rows x all channels
+    const size_t xb = stem ? (size_t)((sp.box_bytes + 127) & ~127) : (size_t)kFqKC * kBM * 4;
     if (fq) {
         // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
-        // (fused stem: a slot holds the rows of a whole tile, four slots cover the load latency; the rest goes to A/B stages)
-        int xs = stem ? 4 : kMaxXStages;
+        // (fused stem: up to kMaxBoxes row boxes in flight — several tiles ahead, the load latency is ~2 tile times)
+        int xs = stem ? kMaxBoxes : kMaxXStages;
         while (xs > 3 && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
@@ -1690,7 +1735,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_REQUIRE(r == CUDA_SUCCESS, QB200_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     }
 
-    const size_t smem = (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + (fq ? prm.x_stages * xb : 0) +
+    const size_t smem = b_res + (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + (fq ? prm.x_stages * xb : 0) +
                         1024 /*align*/ + tail;
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a function: one flag per device (a thread
     // that moves from cuda:0 to cuda:1 must set it again; setting it twice from racing threads is harmless)
@@ -1724,10 +1769,10 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         return 0;
     }
     if (stem) {
-        // fp32 input as (W, H, C, N); box = whole rows x st_rows_box rows x all channels of one image, zero fill outside
+        // fp32 input as (W, H, C, N); box = whole rows x `stride` rows x all channels of one image, zero fill outside
         cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.C, (cuuint64_t)g.N};
         cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.H * g.W * 4, (cuuint64_t)g.C * g.H * g.W * 4};
-        cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)sp.rows_box, (cuuint32_t)g.C, 1};
+        cuuint32_t box[4] = {(cuuint32_t)g.W, (cuuint32_t)g.stride, (cuuint32_t)g.C, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = api.tiled(&tmap_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x_fused), dims, strides, box,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
