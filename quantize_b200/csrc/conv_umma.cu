@@ -434,8 +434,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const bool halo = !kFQ && !kPair && prm.halo != 0;
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
     const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = (kPair ? BN / 2 : BN) * KC,
-                   stage_bytes = kStem ? a_bytes : (halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes);
-    // fused stem: the whole weight matrix (cblocks tiles) stays resident in front of the ring; a stage is an A tile only
+                   stage_bytes = kStem ? a_bytes * (uint32_t)prm.cblocks : (halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes);
+    // fused stem: the whole weight matrix (cblocks tiles) stays resident in front of the ring; a stage is a whole A tile
+    // (all k-blocks: one barrier round trip per tile)
     uint8_t* const bres = smem;
     if constexpr (kStem) smem += (size_t)prm.cblocks * b_bytes;
     uint8_t* xring = smem + (size_t)stages * stage_bytes;                       // fused-quantize: [x_stages][KC][128] fp32
@@ -609,7 +610,21 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + (uint32_t)(buf * prm.acc_stride);
             uint32_t accumulate = 0;
-            if (halo) {
+            if constexpr (kStem) {
+                // one stage = the tile's whole A operand; weights resident
+                mbar_wait(&full[stage], phase, prm.err_flag, 3);
+                tc_fence_after();
+                if (lane == 0) {
+                    for (int kb = 0; kb < cblocks; ++kb) {
+                        const uint32_t a0 = (stage_lo + (uint32_t)kb * a16) | lo_flag, b0 = (bres16 + (uint32_t)kb * (b_bytes >> 4)) | lo_flag;
+                        umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, kb ? 1u : 0u);
+                        umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                stage_lo += stage16;
+                if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
+            } else if (halo) {
                 for (int cb = 0; cb < cblocks; ++cb) {
                     mbar_wait(&xfull[hs], hphase, prm.err_flag, 7);
                     const uint32_t halo_lo = xring16 + (uint32_t)hs * x16;
@@ -772,10 +787,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // quantizes them exactly like the standalone quantizer (quant_math.cuh) and stores four 8-byte channel vectors.
         const QuantParams qp = load_params(prm.q_scale, prm.q_zero, prm.q_qmin, prm.q_qmax);
         if constexpr (kStem) {
-            // ---- fused stem: fp32 input rows -> quantized byte planes -> grouped im2col rows (the A k-blocks) ----
-            // The planes are a ring of st_ring input rows per channel (slot = (row + pad) mod st_ring): consecutive tiles of
-            // the CTA's run share all but ~2 of their input rows, so each row is quantized once per run, not once per tile
-            // (re-quantizing the 9-11 rows of every tile made the kernel instruction-bound: 720 us instead of 450).
+            // ---- fused stem: fp32 input rows -> quantized byte planes -> grouped im2col rows (the A tile) ----
+            // The planes are a ring of st_ring input rows per channel: consecutive tiles of the CTA's run share all but ~2 of
+            // their input rows, so each row is quantized once per run, not once per tile (re-quantizing the 9-11 rows of
+            // every tile made the kernel instruction-bound: 720 us instead of 450).  The warps' per-tile instruction chain
+            // (~350 dependent-ish instructions at ~8 cycles each) is what bounds the kernel — not bytes, not issue slots — so
+            // the loop is software-pipelined: the rows of tile t+1 are quantized BEFORE tile t is built (their box waits are
+            // off the critical path), one block barrier per tile, one A stage (all k-blocks) and one arrival per tile.
             const int qw = warp - (3 + kEpiWarps);          // 0..7
             const int qt = qw * 32 + lane;                  // 0..255
             uint32_t* plane32 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + kTailBytes + 2 * prm.wcls_smem);
@@ -793,8 +811,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t a_row = (uint32_t)(row * kFqKC), ch0 = ((uint32_t)(2 * gh) ^ swz) << 4, ch1 = ((uint32_t)(2 * gh + 1) ^ swz) << 4;
             int xs = 0, stage = 0;
             uint32_t xphase = 0, phase = 0;
-            int cur_img = -1, h_done = 0;                   // input rows [.., h_done) of image cur_img are in the ring
-            for (int tile = unit0; tile < total_tiles; ++tile) {
+            // quantizer stream state: input rows [.., h_done) of image cur_img are in the ring; row ih lives in slot
+            // (ih + ring_off) & rmask, slots are handed out consecutively across images
+            int cur_img = -1, h_done = 0, ring_off = 0;
+            // this thread's first two quads of a box: (line = channel * stride + row of the box, quad of 4 columns)
+            const int nq = g.C * g.stride * W4;
+            const int ln0 = qt < nq ? qt / W4 : -1, j0 = qt - max(ln0, 0) * W4, c0 = max(ln0, 0) / g.stride;
+            const int qt1 = qt + kFqWarps * 32;
+            const int ln1 = qt1 < nq ? qt1 / W4 : -1, j1 = qt1 - max(ln1, 0) * W4, c1 = max(ln1, 0) / g.stride;
+            auto quantize_tile = [&](int tile) -> int {     // returns the tile's ring_off
                 const int m_tile = prm.fd_ntiles.div(tile);
                 const int img = prm.fd_tpi.div(m_tile), t = m_tile - img * prm.tiles_per_img;
                 const int pq0 = t * kBM;
@@ -802,78 +827,114 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 const int p_last = prm.fd_q.div(min(pq0 + kBM, PQs) - 1);
                 const int h0 = p_first * g.stride - g.pad;
                 const int h_end = p_last * g.stride - g.pad + g.R;
-                if (img != cur_img) { cur_img = img; h_done = h0; }
+                if (img != cur_img) {
+                    ring_off = (cur_img < 0 ? 0 : h_done + ring_off) - h0;   // the new image's first row takes the next free slot
+                    cur_img = img;
+                    h_done = h0;
+                }
                 const int h_new = max(h_done, h0), n_new = h_end - h_new;     // rows to quantize now
                 h_done = h_end;
-                // quantize the new rows, box by box (`stride` rows x all channels each): a warp takes whole (channel, row)
-                // lines of the box, a lane 4 consecutive columns
+                // box by box (`stride` rows x all channels each): a warp takes whole (channel, row) lines, a lane 4 columns
                 for (int b0 = 0; b0 < n_new; b0 += g.stride) {
                     mbar_wait(&bfull[xs], xphase, prm.err_flag, 7);
                     const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes);
                     if (!(prm.st_dbg & 1)) {
-                        for (int ln = qw; ln < g.C * g.stride; ln += kFqWarps) {
-                            const int c = g.stride == 1 ? ln : (g.stride == 2 ? ln >> 1 : ln / g.stride), rin = ln - c * g.stride;
+                        // the box's quads (4 columns of one (channel, row) line) spread evenly over the 256 threads
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            const int ln = u ? ln1 : ln0, j = u ? j1 : j0;
+                            if (ln < 0) continue;
+                            const int c = u ? c1 : c0, rin = ln - c * g.stride;
                             const int ih = h_new + b0 + rin;
                             if (ih >= h_end) continue;                         // (a box may reach past the tile's last row)
-                            const float* xl = xt + ln * g.W;
-                            uint32_t* pl = plane32 + (c * ring + ((ih + g.pad) & rmask)) * Wq4 + m4;
+                            uint32_t word = 0u;
                             if ((unsigned)ih < (unsigned)g.H) {
-                                for (int j = lane; j < W4; j += 32) {
-                                    const float4 v = lds4(xl + 4 * j);
-                                    pl[j] = quant_word(v.x, v.y, v.z, v.w, qp);
-                                }
-                            } else {
-                                for (int j = lane; j < W4; j += 32) pl[j] = 0u;
+                                const float4 v = lds4(xt + ln * g.W + 4 * j);
+                                word = quant_word(v.x, v.y, v.z, v.w, qp);
                             }
+                            plane32[(c * ring + ((ih + ring_off) & rmask)) * Wq4 + m4 + j] = word;
+                        }
+                        for (int q2 = qt + 2 * kFqWarps * 32; q2 < g.C * g.stride * W4; q2 += kFqWarps * 32) {   // (wider boxes: generic tail)
+                            const int ln = q2 / W4, j = q2 - ln * W4, c = ln / g.stride, rin = ln - c * g.stride;
+                            const int ih = h_new + b0 + rin;
+                            if (ih >= h_end) continue;
+                            uint32_t word = 0u;
+                            if ((unsigned)ih < (unsigned)g.H) {
+                                const float4 v = lds4(xt + ln * g.W + 4 * j);
+                                word = quant_word(v.x, v.y, v.z, v.w, qp);
+                            }
+                            plane32[(c * ring + ((ih + ring_off) & rmask)) * Wq4 + m4 + j] = word;
                         }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&bempty[xs]);     // this warp has read its part of the box
                     if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
                 }
-                qbar();                                      // planes complete
-                // this thread's output pixel: window origin inside the planes
-                const int pq = min(pq0 + row, PQs - 1);
+                return ring_off;
+            };
+            int off_next = unit0 < total_tiles ? quantize_tile(unit0) : 0;
+            qbar();
+            for (int tile = unit0; tile < total_tiles; ++tile) {
+                const int off = off_next;
+                if (tile + 1 < total_tiles) off_next = quantize_tile(tile + 1);   // one tile ahead of the build
+                // ---- build tile `tile`: this thread's output pixel, window origin inside the planes ----
+                const int m_tile = prm.fd_ntiles.div(tile);
+                const int t = m_tile - prm.fd_tpi.div(m_tile) * prm.tiles_per_img;
+                const int pq = min(t * kBM + row, PQs - 1);
                 const int pi = prm.fd_q.div(pq), qi = pq - pi * g.Q;
                 const int col = qi * g.stride - g.pad + prm.st_margin;      // first byte of the 8-byte windows
                 const uint32_t wcol = plane_s + (uint32_t)(col & ~3);
                 const int sh = (col & 3) * 8;
-                const int slot0 = pi * g.stride;                            // ring slot of filter row 0 (before the mask)
+                const int slot0 = pi * g.stride - g.pad + off;              // ring slot of filter row 0 (before the mask)
                 uint32_t rb[7];                                             // shared address of the window in filter row rf, channel 0
 #pragma unroll
                 for (int rf = 0; rf < 7; ++rf) rb[rf] = wcol + (uint32_t)(((slot0 + rf) & rmask) * Wq4) * 4u;
+                mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
+                const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes + a_row;   // (smem = ring base, past the resident weights)
                 // groups of this thread in k-block kb: gi = 8 * kb + 4 * gh + j  ->  channel gi / 7, filter row gi % 7 (R == 7)
                 auto build = [&](auto gh_tag) {
                     constexpr int GH = decltype(gh_tag)::value;
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb) {
                         if (kb < prm.cblocks) {
-                            mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
-                            const uint32_t sa = smem_u32(smem) + (uint32_t)stage * stage_bytes + a_row;   // (smem = ring base, past the resident weights)
+                            // the 12 loads of the k-block's four windows in ONE asm statement: volatile asm statements keep
+                            // their order, so per-group statements exposed a shared-memory latency per group
+                            uint32_t a[4];
+                            bool ok[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const int gi = kb * 8 + GH * 4 + j;
                                 const int c = gi / 7, rf = gi % 7;
-                                if (c < g.C && !(prm.st_dbg & 2)) {                              // (bytes past the last group meet zero weights)
-                                    const uint32_t a = rb[rf] + (uint32_t)c * cplane;
-                                    uint32_t w0, w1, w2;
-                                    asm volatile("ld.shared.u32 %0, [%3];\n\tld.shared.u32 %1, [%3+4];\n\tld.shared.u32 %2, [%3+8];"
-                                                 : "=r"(w0), "=r"(w1), "=r"(w2) : "r"(a));
-                                    const uint32_t dst = sa + (j < 2 ? ch0 : ch1) + (uint32_t)((j & 1) << 3);
-                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(__funnelshift_r(w0, w1, sh)),
-                                                 "r"(__funnelshift_r(w1, w2, sh)) : "memory");
+                                ok[j] = c < g.C && !(prm.st_dbg & 2);        // (bytes past the last group meet zero weights)
+                                a[j] = ok[j] ? rb[rf] + (uint32_t)c * cplane : rb[0];
+                            }
+                            uint32_t w[4][3];
+                            asm volatile(
+                                "ld.shared.u32 %0, [%12];\n\tld.shared.u32 %1, [%12+4];\n\tld.shared.u32 %2, [%12+8];\n\t"
+                                "ld.shared.u32 %3, [%13];\n\tld.shared.u32 %4, [%13+4];\n\tld.shared.u32 %5, [%13+8];\n\t"
+                                "ld.shared.u32 %6, [%14];\n\tld.shared.u32 %7, [%14+4];\n\tld.shared.u32 %8, [%14+8];\n\t"
+                                "ld.shared.u32 %9, [%15];\n\tld.shared.u32 %10, [%15+4];\n\tld.shared.u32 %11, [%15+8];"
+                                : "=r"(w[0][0]), "=r"(w[0][1]), "=r"(w[0][2]), "=r"(w[1][0]), "=r"(w[1][1]), "=r"(w[1][2]), "=r"(w[2][0]),
+                                  "=r"(w[2][1]), "=r"(w[2][2]), "=r"(w[3][0]), "=r"(w[3][1]), "=r"(w[3][2])
+                                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]));
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                if (ok[j]) {
+                                    const uint32_t dst = sa + (uint32_t)kb * a_bytes + (j < 2 ? ch0 : ch1) + (uint32_t)((j & 1) << 3);
+                                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(dst), "r"(__funnelshift_r(w[j][0], w[j][1], sh)),
+                                                 "r"(__funnelshift_r(w[j][1], w[j][2], sh)) : "memory");
                                 }
                             }
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(&full[stage]);
-                            if (++stage == stages) { stage = 0; phase ^= 1; }
                         }
                     }
                 };
                 if (gh == 0) build(std::integral_constant<int, 0>{});
                 else build(std::integral_constant<int, 1>{});
-                qbar();                                      // new rows may replace ring slots the slowest warp still reads
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+                if (++stage == stages) { stage = 0; phase ^= 1; }
+                qbar();   // rows of tile + 1 complete before its build; this build complete before rows of tile + 2 reuse slots
             }
         } else {
         // All quantizer warps work on the same k-block (every barrier sees every phase: no parity aliasing):
@@ -1440,11 +1501,11 @@ bool stem_plan(const ConvGeom& g, StemPlan* out) {
     const int need = std::max(sp.margin + g.W + g.pad, (g.Q - 1) * g.stride - g.pad + sp.margin + 12);
     sp.Wq = (need + 3) & ~3;
     sp.box_bytes = g.C * g.stride * g.W * 4;               // one TMA box: `stride` input rows of every channel
-    sp.ring = 8;
-    while (sp.ring < sp.rows_box) sp.ring <<= 1;           // ring of input rows per channel plane (a power of two)
+    sp.ring = 8;                                            // ring of input rows per channel plane (a power of two): the rows
+    while (sp.ring < sp.rows_box + rows_out * g.stride) sp.ring <<= 1;   // of a tile plus those quantized ahead for the next
     sp.plane_bytes = (g.C * sp.ring * sp.Wq + 15) & ~15;
     if (im2col8_row_bytes(g.C, g.R) > 4 * kFqKC) return false;
-    if (sp.rows_box > 256 || sp.box_bytes > 24 * 1024 || sp.plane_bytes > 16 * 1024) return false;
+    if (sp.rows_box > 256 || sp.box_bytes > 24 * 1024 || sp.plane_bytes > 32 * 1024) return false;
     if (out) *out = sp;
     return true;
 }
@@ -1581,7 +1642,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
         else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
     }
-    const size_t stage_bytes = stem ? (size_t)kBM * prm.KC
+    const size_t stage_bytes = stem ? (size_t)kBM * prm.KC * prm.cblocks
                                     : (halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC);
     const size_t b_res = stem ? (size_t)prm.cblocks * BN * prm.KC : 0;   // fused stem: the weights stay resident, stages hold A only
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
