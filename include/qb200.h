@@ -309,6 +309,11 @@ int qb200_kthvalue_f32(const float* x, int64_t A, int64_t R, int64_t B, int32_t 
 int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, int32_t W, int32_t kernel, int32_t stride,
                         int32_t pad, float* out, void* stream);
 
+/* Global average pooling of fp32 planes: out[plane] = sum(x[plane][0..HW)) / HW — the op between the last residual stage
+ * and the classifier (torchvision resnet.py: AdaptiveAvgPool2d((1, 1)); the reference runs the torch module there).
+ * One warp per plane; sums in a fixed lane-strided + shuffle-tree order (deterministic, within fp32 rounding of torch). */
+int qb200_avgpool_global_f32(const float* x, int64_t planes, int32_t HW, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,7 @@ SYMBOLS = [
     "qb200_conv_workspace_bytes", "qb200_act_quantize_nhwc", "qb200_set_conv_algo", "qb200_get_conv_algo",
     "qb200_quantconv2d_fused", "qb200_conv2d_q8_nhwc", "qb200_quantconv2d_weightonly",
     "qb200_conv_quantize_input", "qb200_conv_from_workspace", "qb200_conv_is_single_kernel", "qb200_watchdog_code",
-    "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_quantlinear_weightonly", "qb200_fake_quantize_f32",
+    "qb200_quantconv2d_fused_ex", "qb200_conv_from_workspace_ex", "qb200_conv_handoff_supported", "qb200_maxpool2d_f32", "qb200_avgpool_global_f32", "qb200_quantlinear_weightonly", "qb200_fake_quantize_f32",
     "qb200_unpack_act_nhwc", "qb200_dequant_packed_f32", "qb200_quantconv2d_packed", "qb200_quantconv2d_packed_workspace_bytes",
     "qb200_quantlinear_packed", "qb200_minmax_f32", "qb200_minmax_workspace_bytes", "qb200_kthvalue_f32",
     "qb200_kthvalue_workspace_bytes", "qb200_set_rows_chunk", "qb200_conv_rows_chunk",
@@ -92,6 +92,7 @@ def lib():
         L.qb200_conv_from_workspace_ex.argtypes = [sp, vp, vp, vp, i32, vp, ap, ctypes.POINTER(ConvTail), vp, i32, vp]
         L.qb200_conv_handoff_supported.argtypes = [sp, sp]
         L.qb200_maxpool2d_f32.argtypes = [vp, i64, i32, i32, i32, i32, i32, vp, vp]
+        L.qb200_avgpool_global_f32.argtypes = [vp, i64, i32, vp, vp]
         L.qb200_fake_quantize_f32.argtypes = [vp, i64, ap, vp, vp]
         L.qb200_quantlinear_weightonly.argtypes = [vp, i64, i32, i32, vp, i32, i32, vp, vp, i32, vp, vp, vp]
         f32 = ctypes.c_float

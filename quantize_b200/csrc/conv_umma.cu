@@ -156,6 +156,9 @@ __device__ __forceinline__ void sts2(void* p, uint32_t a, uint32_t b) {
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -1030,27 +1033,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                        e * (kResDepth * kResChunkFloats);
         struct { int tile, c, kb; bool live, pix_ok; const float* base; } cur = {0, 0, 0, false, false, nullptr};
         int issue_slot = 0, cons_slot = 0;
+        // res_async == 2: planes whose size is not a multiple of 4 pixels (7x7: 49) — 16-byte pieces do not line up, so a
+        // lane copies its own pixel of every channel with 4-byte cp.async (32 per chunk instead of 8)
+        const bool res4 = kRes && prm.res_async == 2;
         auto cur_set_tile = [&](int t) {
             cur.tile = t;
             cur.c = 0;
             cur.live = t < total_tiles;
             if (cur.live) {
                 const int mt = prm.fd_ntiles.div(t), nt = t - mt * prm.n_tiles;
-                const int64_t m = (int64_t)mt * kBM + quad * 32 + 4 * (lane & 7);
+                const int64_t m = (int64_t)mt * kBM + quad * 32 + (res4 ? lane : 4 * (lane & 7));
                 cur.pix_ok = m < prm.M;
                 const int im = cur.pix_ok ? prm.fd_pq.div((int)m) : 0;
-                cur.kb = nt * BN + half * cols + (lane >> 3);
+                cur.kb = nt * BN + half * cols + (res4 ? 0 : (lane >> 3));
                 cur.base = ep.residual + ((int64_t)im * g.K + cur.kb) * PQ + (int)(m - (int64_t)im * PQ);
             }
         };
         auto issue_one = [&]() {  // next chunk of the stream (if any); always one commit group per call
             if (cur.live) {
-                float* dst = res_s + issue_slot * kResChunkFloats + (lane >> 3) * 32 + 4 * (lane & 7);
                 const float* src = cur.base + (int64_t)cur.c * 32 * PQ;
                 const int k = cur.kb + cur.c * 32;
+                if (res4) {
+                    float* dst = res_s + issue_slot * kResChunkFloats + lane;
+                    if (cur.pix_ok) {
+#pragma unroll 8
+                        for (int i = 0; i < 32; ++i)
+                            if (k + i < g.K) cp_async4(dst + i * 32, src + (int64_t)i * PQ);
+                    }
+                } else {
+                    float* dst = res_s + issue_slot * kResChunkFloats + (lane >> 3) * 32 + 4 * (lane & 7);
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (cur.pix_ok && k + 4 * i < g.K) cp_async16(dst + i * 128, src + (int64_t)i * 4 * PQ);
+                    for (int i = 0; i < 8; ++i)
+                        if (cur.pix_ok && k + 4 * i < g.K) cp_async16(dst + i * 128, src + (int64_t)i * 4 * PQ);
+                }
                 if (++cur.c == (cols >> 5)) cur_set_tile(cur.tile + (int)gridDim.x);
             }
             cp_async_commit();
@@ -1689,11 +1704,17 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     }
     // residual tail: stream the identity through per-warp cp.async rings when 16-byte pieces line up (4 pixels of one
     // image and channel) and two operand stages still fit next to the 96 KB of rings
+    // (planes that are not a multiple of 4 pixels — 7x7 — use 4-byte copies: res_async == 2; QB200_RES4=0 turns that off)
     prm.res_async = 0;
-    if (!fq && !halo && !pair && ep.residual != nullptr && ep.out_kind == QB200_OUT_F32 && (g.P * g.Q) % 4 == 0 &&
-        reinterpret_cast<uintptr_t>(ep.residual) % 16 == 0 && prm.M < (1ll << 31) &&
-        kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq)
-        prm.res_async = 1;
+    static const bool res4_on = [] {
+        const char* e = getenv("QB200_RES4");
+        return !(e && e[0] == '0');
+    }();
+    if (!fq && !halo && !pair && ep.residual != nullptr && ep.out_kind == QB200_OUT_F32 && prm.M < (1ll << 31) &&
+        kTailBytes + 2 * (size_t)prm.wcls_smem + kResBytes + 2 * stage_bytes + 1024 <= kSmemBudgetFq) {
+        if ((g.P * g.Q) % 4 == 0 && reinterpret_cast<uintptr_t>(ep.residual) % 16 == 0) prm.res_async = 1;
+        else if (res4_on && reinterpret_cast<uintptr_t>(ep.residual) % 4 == 0) prm.res_async = 2;
+    }
     const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0) + (stem ? (size_t)sp.plane_bytes : 0);
     size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail - b_res;
     // ring slot of the fp32 input: a [64 channels][128 pixels] tile, or (fused stem) one box of `stride` rows x all channels

@@ -673,6 +673,21 @@ at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int paddi
     return out;
 }
 
+// avg_pool_global (engine helper: AdaptiveAvgPool2d((1, 1)) of the packed ResNet forward) -> [N, C, 1, 1]
+at::Tensor avg_pool_global(const at::Tensor& input) {
+    CHECK_INPUT(input);
+    CHECK_FLOAT(input);
+    TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
+    TORCH_CHECK(input.size(2) * input.size(3) >= 1, "avg_pool_global: empty planes");
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(input.device());
+    auto out = at::empty({input.size(0), input.size(1), 1, 1}, input.options());
+    check_rc(qb200_avgpool_global_f32(input.data_ptr<float>(), input.size(0) * input.size(1), (int)(input.size(2) * input.size(3)),
+                                      out.data_ptr<float>(), cur_stream()),
+             "avg_pool_global");
+    return out;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Calibration reductions (reference range/minmax.py:62-108, :44-60, :184-203).
 //   minmax(x, granularity, flag, symmetric, update_mode=0, momentum=0.0, run_min=None, run_max=None) -> (xmin, xmax)
@@ -978,6 +993,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           py::arg("input"), py::arg("scale"), py::arg("zero"), py::arg("qmin"), py::arg("qmax"));
     m.def("max_pool2d", &max_pool2d, "fp32 NCHW max pooling (square kernel / stride, -inf padding, floor mode).",
           py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0);
+    m.def("avg_pool_global", &avg_pool_global, "fp32 NCHW global average pooling -> [N, C, 1, 1].", py::arg("input"));
     m.def("minmax", &minmax, "The range estimators' (xmin, xmax) in one pass, with the optional running / moving-average update.",
           py::arg("input"), py::arg("granularity"), py::arg("flag"), py::arg("symmetric"), py::arg("update_mode") = 0,
           py::arg("momentum") = 0.0, py::arg("run_min") = py::none(), py::arg("run_max") = py::none());

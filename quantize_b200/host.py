@@ -402,6 +402,15 @@ class EngineMaxPool2d(nn.Module):
         return torch.nn.functional.max_pool2d(x, self.kernel_size, self.stride, self.padding)
 
 
+class EngineGlobalAvgPool2d(nn.Module):
+    """nn.AdaptiveAvgPool2d((1, 1)) on the engine's kernel (one warp per plane); torch's op elsewhere."""
+
+    def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float32 and x.dim() == 4:
+            return _engine.load().avg_pool_global(x.contiguous())
+        return torch.nn.functional.adaptive_avg_pool2d(x, (1, 1))
+
+
 def _chainable(convs):
     """int8 hand-off between consecutive convs needs the engine path, symmetric weights (w_zero == 0) and activation
     ranges that fit an unsigned byte."""
@@ -594,4 +603,8 @@ def pack(model):
     for m in model.modules():
         if isinstance(m, (QuantConv2d, QuantLinear)):
             m.pack()
+    # the packed model runs on the engine: its global average pool too (torch's generic reduction is 4x slower there)
+    pool = getattr(model, "avgpool", None)
+    if isinstance(pool, nn.AdaptiveAvgPool2d) and pool.output_size in (1, (1, 1)):
+        model.avgpool = EngineGlobalAvgPool2d()
     return model

@@ -210,3 +210,18 @@ def test_fake_quantize_matches_the_torch_ops(engine, rng_, n):
     y = x[1:].contiguous()[: (n - 1) // 2 * 2].view(-1, 2) if n > 4 else x.view(1, 1)
     assert torch.equal(engine.fake_quantize(y, scale, zero, qmin, qmax).nan_to_num(0.0),
                        ((torch.clamp(torch.round(y / scale - zero), qmin, qmax) + zero) * scale).nan_to_num(0.0))
+
+
+@pytest.mark.parametrize("shape", [(3, 2048, 7, 7), (2, 5, 1, 1), (1, 7, 33, 9), (4, 64, 14, 14)])
+def test_avg_pool_global_matches_torch(engine, shape):
+    """engine.avg_pool_global == adaptive_avg_pool2d(x, (1, 1)) within fp32 summation-order rounding; float64 mean as the
+    referee (the engine's fixed-order sum must be at least as close to it as 2 ulps of the plane's absolute mean)."""
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).cuda()
+    got = engine.avg_pool_global(x)
+    want = torch.nn.functional.adaptive_avg_pool2d(x, (1, 1))
+    exact = x.double().mean(dim=(2, 3), keepdim=True)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    tol = 4 * torch.finfo(torch.float32).eps * x.abs().double().mean(dim=(2, 3), keepdim=True) + 1e-12
+    assert ((got.double() - exact).abs() <= tol).all()
+    assert torch.allclose(got, want, rtol=1e-5, atol=1e-6)

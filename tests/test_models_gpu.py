@@ -191,8 +191,10 @@ def test_fused_tail_op_level(engine):
     """quantconv2d_float_input(..., residual=, fuse_relu=) == relu(op(...) + residual), both conv kernels."""
     from gpu_util import random_conv_case
     import numpy as np
+    # (planes of 49 / 81 / 289 pixels are not a multiple of 4: the identity stream uses 4-byte copies there)
     for cfg in ((2, 64, 14, 14, 64, 3, 1, 1, 1), (2, 64, 28, 28, 256, 1, 1, 0, 1), (2, 3, 33, 33, 64, 7, 2, 3, 1),
-                (2, 32, 8, 8, 32, 3, 1, 1, 32)):
+                (2, 32, 8, 8, 32, 3, 1, 1, 32), (5, 128, 7, 7, 512, 1, 1, 0, 1), (3, 64, 7, 7, 128, 3, 1, 1, 1),
+                (2, 64, 9, 9, 96, 1, 1, 0, 1)):
         N, C, H, W, K, R, stride, pad, groups = cfg
         c = random_conv_case(sum(cfg), N, C, H, W, K, R, stride, pad, groups)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
