@@ -338,6 +338,10 @@ std::shared_ptr<PreparedWeights> prepared_weights(const qb200_conv_shape& s, con
     // first use on another stream: order it after the preparation (once the event has completed no wait is needed any
     // more — this also keeps replays / stream captures free of cross-stream waits)
     if (pw->stream != static_cast<cudaStream_t>(st) && !pw->settled.load(std::memory_order_acquire)) {
+        // cudaEventQuery / waits on outside events are illegal while a stream captures: a capture is preceded by a warm-up
+        // and a device synchronisation (host.GraphedForward, torch.cuda.graph's own contract), so the weights are ready
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(static_cast<cudaStream_t>(st), &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return pw;
         if (pw->ready->query()) pw->settled.store(true, std::memory_order_release);
         else pw->ready->block(at::cuda::getCurrentCUDAStream());
     }

@@ -338,3 +338,20 @@ def test_resnet50_w8a8_batch256_full_size():
 
 def test_mobilenet_v2_w4a8_batch128_full_size():
     _full_size_parity("mobilenet_v2", 128, 4, 8, chain=False)
+
+
+def test_graphed_forward_on_a_fresh_model_equals_eager():
+    """host.GraphedForward right after build_packed (no eager call first): the prepared weights are created by the
+    warm-up on a side stream and first used by the capture on another stream — no event query / wait may happen inside
+    the capture.  Replays of both input buffers == the eager forward, bit for bit."""
+    net = models.build_packed("resnet18", 8, 8, calib_batch=4, device="cuda", seed=0, fuse_blocks=True, chain_blocks=True,
+                              cross_block=True)
+    x = models.synthetic_batch("resnet18", 4, device="cuda")
+    g = host.GraphedForward(net, torch.zeros_like(x), n_buffers=2)
+    outs = []
+    for i in range(2):
+        g.input(i).copy_(x)
+        outs.append(g(i).clone())
+    with torch.no_grad():
+        want = net(x)
+    assert torch.equal(outs[0], want) and torch.equal(outs[1], want)
