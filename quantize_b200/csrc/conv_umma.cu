@@ -58,6 +58,7 @@ constexpr size_t kSmemBudget = 200 * 1024;
 constexpr int kResDepth = 3;                            // residual chunks in flight per epilogue warp (cp.async ring)
 constexpr int kResChunkFloats = 32 * 32;                // one chunk: 32 channels x 32 pixels
 constexpr size_t kResBytes = (size_t)kEpiWarps * kResDepth * kResChunkFloats * 4;  // 96 KB
+constexpr int kAStatBar = 12;        // A-stationary mode: barriers of the A ring = full / empty[kAStatBar ..] (weight stages < kAStatBar)
 constexpr size_t kSmemBudgetFq = 224 * 1024;  // the fused-quantize variant wants every byte for fp32 tiles in flight
 
 // Division of a non-negative 32-bit value by a launch-time constant as one multiply-high + shift: the per-tile index
@@ -112,6 +113,10 @@ struct UmmaParams {
     int halo;          // 0/1
     int Hp, Wp, halo_rows, halo_bytes, h_stages;
     int x_stages;  // fused-quantize variant: slots of the fp32 ring
+    // A-stationary fused quantize (1x1 layers with several channel tiles): a CTA owns whole pixel tiles and runs ALL their
+    // channel tiles back to back; the quantized A k-blocks live in their own ring of a_slots slots (behind the fp32 ring),
+    // are written once per pixel tile and released by the MMAs of the LAST channel tile; stages then hold weights only
+    int a_stat, a_slots;
     int n_acc, acc_stride;  // TMEM accumulator buffers and the columns between them
     int res_async;          // residual tail: stream the identity tensor through a per-warp cp.async ring
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
@@ -436,8 +441,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     static_assert(!kStem || kFQ, "the fused stem is a producer mode of the fused-quantize kernel");
     const bool halo = !kFQ && !kPair && prm.halo != 0;
     const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;      // 0 = leader (issues the MMAs)
+    const bool a_stat = kFQ && !kStem && prm.a_stat != 0;
     const uint32_t a_bytes = halo ? 0u : (uint32_t)(kBM * KC), b_bytes = (kPair ? BN / 2 : BN) * KC,
-                   stage_bytes = kStem ? a_bytes * (uint32_t)prm.cblocks : (halo ? b_bytes * (uint32_t)prm.tap_group : a_bytes + b_bytes);
+                   stage_bytes = kStem ? a_bytes * (uint32_t)prm.cblocks
+                                       : (halo ? b_bytes * (uint32_t)prm.tap_group : (a_stat ? b_bytes : a_bytes + b_bytes));
     // fused stem: the whole weight matrix (cblocks tiles) stays resident in front of the ring; a stage is a whole A tile
     // (all k-blocks: one barrier round trip per tile)
     uint8_t* const bres = smem;
@@ -446,7 +453,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t x_bytes = kStem ? (uint32_t)prm.st_box_pitch
                                    : (kFQ ? (uint32_t)KC * kBM * 4u : (halo ? (uint32_t)prm.halo_bytes : 0u));  // ring slot size
     const int x_slots = kFQ ? prm.x_stages : (halo ? prm.h_stages : 0);       // fp32 tiles (kFQ) or u8 halo tiles (halo)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(xring + (size_t)x_slots * x_bytes);
+    uint8_t* const aring = xring + (size_t)x_slots * x_bytes;                  // A-stationary: [a_slots][128][KC] u8
+    uint64_t* bars = reinterpret_cast<uint64_t*>(aring + (a_stat ? (size_t)prm.a_slots * a_bytes : 0));
     uint64_t* full = bars;                     // [stages]
     uint64_t* empty = bars + kMaxStages;       // [stages]
     uint64_t* acc_full = bars + 2 * kMaxStages;               // [kMaxAcc]
@@ -463,19 +471,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int lane = threadIdx.x & 31;
     // work units: tiles, round-robin over the CTAs — or, for the pair variant, 256-pixel pair tiles over the CTA pairs
     // (fused stem: every CTA takes a CONTIGUOUS run of tiles, so that consecutive tiles share quantized input rows)
+    // (A-stationary: work items are CTA-local — item j = channel tile j % n_tiles of the CTA's (j / n_tiles)-th pixel tile,
+    // pixel tiles round-robin over the CTAs: m_tile = blockIdx.x + (j / n_tiles) * gridDim.x)
     const int all_tiles = kPair ? ((prm.m_tiles + 1) >> 1) * prm.n_tiles : prm.m_tiles * prm.n_tiles;
     const int stem_run = kStem ? (all_tiles + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int total_tiles = kStem ? min(all_tiles, ((int)blockIdx.x + 1) * stem_run) : all_tiles;
-    const int unit0 = kStem ? (int)blockIdx.x * stem_run : (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
-    const int unit_step = kStem ? 1 : (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+    const int my_m = a_stat ? (prm.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_tiles = kStem ? min(all_tiles, ((int)blockIdx.x + 1) * stem_run) : (a_stat ? my_m * prm.n_tiles : all_tiles);
+    const int unit0 = kStem ? (int)blockIdx.x * stem_run : (a_stat ? 0 : (kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x));
+    const int unit_step = (kStem || a_stat) ? 1 : (kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x);
     const int kblocks = gm.R * gm.S * prm.cblocks;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int i = 0; i < stages; ++i) {
-            mbar_init(&full[i], kStem ? kFqWarps : (kFQ ? 1 + kFqWarps : 1));  // TMA expect_tx arrival (+ one arrival per quantizer warp; stem: the warps only)
+            mbar_init(&full[i], kStem ? kFqWarps : ((kFQ && !a_stat) ? 1 + kFqWarps : 1));  // TMA expect_tx arrival (+ one arrival per quantizer warp; stem: the warps only)
             mbar_init(&empty[i], 1);
+        }
+        if (a_stat) {
+            for (int i = 0; i < prm.a_slots; ++i) {
+                mbar_init(&full[kAStatBar + i], kFqWarps);    // one arrival per quantizer warp
+                mbar_init(&empty[kAStatBar + i], 1);          // the commit after the last channel tile's MMAs
+            }
         }
         for (int i = 0; i < kMaxAcc; ++i) {
             mbar_init(&acc_full[i], 1);
@@ -564,7 +581,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         for (int cb = 0; cb < prm.cblocks; ++cb) {
                             mbar_wait<(kFQ && !kStem) ? 200 : 0>(&empty[stage], phase ^ 1, prm.err_flag, 1);
                             uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                            uint8_t* sb = sa + a_bytes;
+                            uint8_t* sb = sa + (a_stat ? 0u : a_bytes);
                             if constexpr (kPair) {
                                 // both CTAs' loads complete on the LEADER's barrier, armed with the bytes of both
                                 const uint32_t lead_bar = mapa_u32(smem_u32(&full[stage]), 0);
@@ -608,6 +625,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t stage_lo = base16;
         if constexpr (kStem) mbar_wait(&xfull[kMaxXStages - 1], 0, prm.err_flag, 3);   // resident weights have landed
         const uint32_t bres16 = smem_u32(bres) >> 4;
+        const uint32_t aring16 = smem_u32(aring) >> 4;
+        int as_base = 0, nn = 0;          // A-stationary: ring slot of the pixel tile's first k-block, channel tile of this item
+        uint32_t as_phase = 0;
         for (int tile = unit0; tile < total_tiles && pair_rank == 0; tile += unit_step) {   // (pair: the leader issues for both)
             mbar_wait<(kFQ && !kStem) ? 200 : 0>(&acc_empty[buf], acc_phase ^ 1, prm.err_flag, 2);
             tc_fence_after();
@@ -694,6 +714,30 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     if (lane == 0) umma_commit(&xempty[hs]);  // halo slot reusable once every tap's MMAs have read it
                     if (++hs == h_stages) { hs = 0; hphase ^= 1; }
                 }
+            } else if (a_stat) {
+                // A k-blocks from their own ring (waited for during the first channel tile, released after the last one);
+                // the stages hold this channel tile's weights
+                const bool first_n = nn == 0, last_n = nn == prm.n_tiles - 1;
+                int as = as_base;
+                uint32_t ap = as_phase;
+                for (int kb = 0; kb < cblocks; ++kb) {
+                    if (first_n) mbar_wait<200>(&full[kAStatBar + as], ap, prm.err_flag, 3);
+                    mbar_wait<200>(&full[stage], phase, prm.err_flag, 3);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a0 = (aring16 + (uint32_t)as * a16) | lo_flag, b0 = stage_lo | lo_flag;
+                        umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
+                        umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);      // KC = 64: two K = 32 slices
+                        umma_commit(&empty[stage]);
+                        if (last_n) umma_commit(&empty[kAStatBar + as]);
+                    }
+                    accumulate = 1;
+                    stage_lo += stage16;
+                    if (++stage == stages) { stage = 0; stage_lo = base16; phase ^= 1; }
+                    if (++as == prm.a_slots) { as = 0; ap ^= 1; }
+                }
+                if (last_n) { as_base = as; as_phase = ap; nn = 0; }
+                else ++nn;
             } else {
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait<(kFQ && !kStem) ? 200 : 0>(&full[stage], phase, prm.err_flag, 3);
@@ -751,8 +795,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             int xs = 0;
             uint32_t xphase = 0;
             int st_img = -1, st_done = 0;
-            for (int tile = kStem ? unit0 : (int)blockIdx.x; tile < total_tiles; tile += kStem ? 1 : (int)gridDim.x) {
-                const int m_tile = tile / prm.n_tiles;
+            for (int tile = (kStem || a_stat) ? unit0 : (int)blockIdx.x; tile < total_tiles;
+                 tile += kStem ? 1 : (a_stat ? prm.n_tiles : (int)gridDim.x)) {     // (A-stationary: once per pixel tile)
+                const int m_tile = a_stat ? (int)blockIdx.x + (tile / prm.n_tiles) * (int)gridDim.x : tile / prm.n_tiles;
                 const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
                 if constexpr (kStem) {
                     // the input rows this tile adds to the ring (same bookkeeping as the quantizer warps), as boxes of
@@ -774,7 +819,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     continue;
                 }
                 for (int cb = 0; cb < prm.cblocks; ++cb) {
-                    prefetch_next();
+                    if (!a_stat) prefetch_next();
                     mbar_wait<200>(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
                     mbar_expect_tx(&xfull[xs], x_bytes);
                     // box [128 pixels][KC channels] of image img; pixels beyond H*W are zero-filled
@@ -948,7 +993,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int rot = lane >> 1;
         int xs = 0, stage = 0;
         uint32_t xphase = 0, phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // (A-stationary: once per pixel tile, into the A ring — `stage` then walks its a_slots slots)
+        const int q_stages = a_stat ? prm.a_slots : stages;
+        uint64_t* const qfull = a_stat ? full + kAStatBar : full;
+        uint64_t* const qempty = a_stat ? empty + kAStatBar : empty;
+        uint8_t* const qbase = a_stat ? aring : smem;
+        const uint32_t q_stride = a_stat ? a_bytes : stage_bytes;
+        for (int tile = a_stat ? 0 : (int)blockIdx.x; tile < total_tiles; tile += a_stat ? prm.n_tiles : (int)gridDim.x) {
             for (int cb = 0; cb < prm.cblocks; ++cb) {
                 mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
                 const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes) + (pw * 8) * kBM + lane * 4;
@@ -962,8 +1013,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // through a third of the issue slots (ncu: 14.6 M NANOSLEEP wake-ups on one layer).
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xempty[xs]);  // this warp's part of the fp32 tile is in registers
-                mbar_wait(&empty[stage], phase ^ 1, prm.err_flag, 5);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                mbar_wait(&qempty[stage], phase ^ 1, prm.err_flag, 5);
+                uint8_t* sa = qbase + (size_t)stage * q_stride;
                 // lanes rotate which of their 4 pixels they store in each step so that one store instruction spreads
                 // over all swizzle phases; SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3.  The rotation is applied
                 // to the registers with selects (a dynamic register index compiles to a branchy loop that cost a third
@@ -991,9 +1042,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the MMA
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full[stage]);
+                if (lane == 0) mbar_arrive(&qfull[stage]);
                 if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
-                if (++stage == stages) { stage = 0; phase ^= 1; }
+                if (++stage == q_stages) { stage = 0; phase ^= 1; }
             }
         }
         }   // !kStem
@@ -1085,7 +1136,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t acc_phase = (uint32_t)(it >> acc_shift) & 1u;
             const int u_tile = prm.fd_ntiles.div(tile);                 // m-tile, or pair of m-tiles
             const int n_tile = tile - u_tile * prm.n_tiles;
-            const int m_tile = kPair ? 2 * u_tile + (int)pair_rank : u_tile;   // (an odd tail: m_tile == m_tiles, no valid rows)
+            const int m_tile = kPair ? 2 * u_tile + (int)pair_rank
+                                     : (a_stat ? (int)blockIdx.x + u_tile * (int)gridDim.x : u_tile);   // (pair, odd tail: m_tile == m_tiles, no valid rows)
             const int k_base = n_tile * BN;
             // ---- per-tile channel constants (once per CTA when there is a single channel tile) ----
             float* sc = consts + (prm.n_tiles > 1 ? (iter & 1) : 0) * kConstFloats;   // two constant buffers, by tile parity
@@ -1540,7 +1592,24 @@ bool umma_stem_supported(const ConvGeom& g, const float* x) {
 // Round 2 (A/B over all 53 layers with the fused variant forced): 1024 -> 256 at 14x14 also wins (72 vs 78 us); layers with
 // several channel tiles (128 -> 512: 113 vs 108 us, 256 -> 1024: 80 vs 72 us) lose because every channel tile quantizes
 // the same pixels again.
+// QB200_ASTAT: 0 = A-stationary mode off (several channel tiles re-quantize, as before), 1 = on (default), 2 = also
+// profitable on 14x14 planes (A/B measurements; the forced fused-quantize algo of the tests takes it on every eligible shape)
+int a_stat_mode() {
+    static const int v = [] {
+        const char* e = getenv("QB200_ASTAT");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+// A-stationary fused quantize: the pixel tile's quantized k-blocks (8 KB each) must fit their ring next to two fp32 slots
+bool a_stat_fits(const ConvGeom& g) { return g.C / kFqKC <= kMaxStages - kAStatBar; }
+
 bool umma_fused_quant_profitable(const ConvGeom& g) {
+    // several channel tiles (K > 256), A-stationary: the pixels are quantized once and the second pass over the input is gone
+    // (128 -> 512 @28x28: 104 vs 108 us).  Not on 14x14 planes: image-aligned 128 + 68-pixel tiles are 512 pixel tiles where
+    // the flat tiling of the two-kernel path has 392, and an output-bound layer pays for every tile's epilogue
+    // (256 -> 1024 @14x14: 79.5 vs 72.5 us).
+    if (g.K > 256 && a_stat_mode() != 0 && a_stat_fits(g) && g.H * g.W >= (a_stat_mode() == 2 ? 196 : 784)) return true;
     if (g.H * g.W >= 784) return g.C == 64 || g.C >= 2 * g.K;
     return g.H * g.W >= 196 && g.C >= 4 * g.K;
 }
@@ -1633,7 +1702,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             if (cost < best_cost) { best_cost = cost; best = cand; }
         }
         BN = best;
-    } else {
+    } else if (!(fq && !stem && a_stat_mode() != 0 && a_stat_fits(g))) {
+        // (fused quantize with the A-stationary mode: a CTA runs all channel tiles of its pixel tiles, narrower tiles add
+        // no parallelism — and without it every extra channel tile quantizes the same pixels again)
         while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
     }
     if (stem) BN = g.K > 128 ? 256 : (g.K > 64 ? 128 : 64);   // one channel tile: the rows are built once per pixel tile
@@ -1657,8 +1728,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
         else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
     }
+    const bool a_stat = fq && !stem && prm.n_tiles > 1 && a_stat_mode() != 0 && a_stat_fits(g);
+    prm.a_stat = a_stat ? 1 : 0;
+    prm.a_slots = 0;
     const size_t stage_bytes = stem ? (size_t)kBM * prm.KC * prm.cblocks
-                                    : (halo ? (size_t)BN * prm.KC * prm.tap_group : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC);
+                                    : (halo ? (size_t)BN * prm.KC * prm.tap_group
+                                            : (a_stat ? (size_t)BN * prm.KC : (size_t)(kBM + (pair ? BN / 2 : BN)) * prm.KC));
     const size_t b_res = stem ? (size_t)prm.cblocks * BN * prm.KC : 0;   // fused stem: the weights stay resident, stages hold A only
     // window classes of the output rows / columns (only layers with a spatial kernel have border pixels)
     prm.wcls_smem = 0;
@@ -1719,11 +1794,24 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail - b_res;
     // ring slot of the fp32 input: a [64 channels][128 pixels] tile, or (fused stem) one box of `stride` rows x all channels
     const size_t xb = stem ? (size_t)((sp.box_bytes + 127) & ~127) : (size_t)kFqKC * kBM * 4;
+    if (a_stat) {
+        // A ring: two pixel tiles' worth of k-blocks when that leaves three fp32 slots and three weight stages, at least
+        // one tile's worth plus a slot of lookahead
+        const size_t a_b = (size_t)kBM * prm.KC;
+        int as = std::min(2 * prm.cblocks, kMaxStages - kAStatBar);
+        while (as > prm.cblocks + 1 && (size_t)as * a_b + 3 * xb + 3 * stage_bytes > ring_budget) --as;
+        if (as < prm.cblocks + 1 && prm.cblocks + 1 <= kMaxStages - kAStatBar) as = prm.cblocks + 1;
+        as = std::max(as, prm.cblocks);
+        QB_REQUIRE((size_t)as * a_b + 2 * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
+                   "conv_umma: A-stationary tile does not fit shared memory");
+        prm.a_slots = as;
+        ring_budget -= (size_t)as * a_b;
+    }
     if (fq) {
         // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
         // (fused stem: up to kMaxBoxes row boxes in flight — several tiles ahead, the load latency is ~2 tile times)
         int xs = stem ? kMaxBoxes : kMaxXStages;
-        while (xs > 3 && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
+        while (xs > (a_stat ? 2 : 3) && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
         prm.x_stages = xs;
@@ -1740,6 +1828,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     }
     int stages = (int)(ring_budget / stage_bytes);
     if (stages > kMaxStages) stages = kMaxStages;
+    if (a_stat && stages > kAStatBar) stages = kAStatBar;
     QB_REQUIRE(stages >= 2, QB200_EUNSUPPORTED, "conv_umma: tile does not fit shared memory");
     QB_REQUIRE(!stem || prm.n_tiles == 1, QB200_EUNSUPPORTED, "conv_umma: the fused stem needs a single channel tile");
     prm.stages = stages;
@@ -1818,7 +1907,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     }
 
     const size_t smem = b_res + (size_t)stages * stage_bytes + (size_t)prm.h_stages * prm.halo_bytes + (fq ? prm.x_stages * xb : 0) +
-                        1024 /*align*/ + tail;
+                        (size_t)prm.a_slots * kBM * prm.KC + 1024 /*align*/ + tail;
     // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a function: one flag per device (a thread
     // that moves from cuda:0 to cuda:1 must set it again; setting it twice from racing threads is harmless)
     static std::atomic<uint64_t> smem_set_mask{0};
@@ -1838,7 +1927,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         QB_CUDA(cudaFuncSetAttribute(conv_umma_kernel<false, false, true, 1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetFq));
         if (cur_dev >= 0 && cur_dev < 64) smem_set_mask.fetch_or(1ull << cur_dev, std::memory_order_release);
     }
-    const int total_tiles = prm.m_tiles * prm.n_tiles;
+    const int total_tiles = a_stat ? prm.m_tiles : prm.m_tiles * prm.n_tiles;   // (A-stationary: a CTA's unit is a pixel tile)
     const int grid = total_tiles < sms ? total_tiles : sms;
     if (pair) {
         const int pair_tiles = ((prm.m_tiles + 1) / 2) * prm.n_tiles;

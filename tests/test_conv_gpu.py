@@ -440,3 +440,32 @@ def test_fused_stem_rows_built_in_shared_memory(cfg):
     assert np.array_equal(acc_s.cpu().numpy(), acc_ref)
     assert torch.equal(acc_s, acc_2) and torch.equal(out_s, out_2)
     assert_close_1e3(out_s.cpu().numpy(), out_ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# A-stationary fused quantize (round 2): 1x1 layers with several channel tiles, pixels quantized once per pixel tile
+# ---------------------------------------------------------------------------------------------------
+ASTAT_CASES = [
+    # N, C, H, W, K
+    (3, 128, 28, 28, 512),      # ResNet-50 layer2 expand: 2 k-blocks, 2 channel tiles, 7 pixel tiles per image (ragged last)
+    (5, 256, 14, 14, 1024),     # layer3 expand: 4 k-blocks, 4 channel tiles, 128 + 68 pixel tiles
+    (2, 64, 8, 8, 320),         # one k-block, ragged last channel tile (320 = 256 + 64), half-empty pixel tile
+    (2, 512, 6, 6, 768),        # 8 k-blocks: the A ring holds one tile plus lookahead, 3 channel tiles
+    (40, 128, 14, 14, 512),     # more pixel tiles than SMs: CTAs run several pixel tiles (ring wrap, phases)
+    (2, 768, 4, 4, 512),        # 12 k-blocks: the ring is exactly one pixel tile
+]
+
+
+@pytest.mark.parametrize("cfg", ASTAT_CASES, ids=lambda c: "N{}C{}H{}W{}K{}".format(*c))
+def test_a_stationary_fused_quantize(cfg):
+    """int32 accumulators bit-exact vs the oracle and vs the two-kernel path; fp32 within 1e-3 and identical to the
+    two-kernel path's (same epilogue arithmetic)."""
+    N, C, H, W, K = cfg
+    c = random_conv_case(sum(cfg), N, C, H, W, K, 1, 1, 0)
+    acc, out = run_case(c, ALGOS["umma"])          # fused quantize forced: K > 256 -> A-stationary
+    acc_2, out_2 = run_case(c, ALGOS["umma2k"])
+    assert torch.equal(acc, acc_2) and torch.equal(out, out_2)
+    if N * H * W * K * C <= 4e9:
+        _, acc_ref, out_ref = oracle_case(c)
+        assert np.array_equal(acc.cpu().numpy(), acc_ref)
+        assert_close_1e3(out.cpu().numpy(), out_ref)
