@@ -787,7 +787,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             auto prefetch_next = [&]() {
                 if (pf_tile >= total_tiles) return;
                 const int m_tile = pf_tile / prm.n_tiles;
-                const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                const int img = m_tile / max(prm.tiles_per_img, 1), t = m_tile - img * prm.tiles_per_img;
                 tma_prefetch_3d(&tmap_a, t * kBM, pf_cb * KC, img);
                 if (++pf_cb == prm.cblocks) { pf_cb = 0; pf_tile += gridDim.x; }
             };
@@ -798,7 +798,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int tile = (kStem || a_stat) ? unit0 : (int)blockIdx.x; tile < total_tiles;
                  tile += kStem ? 1 : (a_stat ? prm.n_tiles : (int)gridDim.x)) {     // (A-stationary: once per pixel tile)
                 const int m_tile = a_stat ? (int)blockIdx.x + (tile / prm.n_tiles) * (int)gridDim.x : tile / prm.n_tiles;
-                const int img = m_tile / prm.tiles_per_img, t = m_tile - img * prm.tiles_per_img;
+                // flat pixel tiling (tiles_per_img == 0): the tile is 128 consecutive pixels of the batch and may end in the
+                // next image — then a second box (same shape, start pixel off0 - H*W < 0: its first H*W - off0 pixels are
+                // zero-filled) goes to the next ring slot and the quantizer threads read their 4 pixels from one or the other
+                const bool flat = !kStem && prm.tiles_per_img == 0;
+                const int img = flat ? prm.fd_pq.div(m_tile * kBM) : m_tile / prm.tiles_per_img;
+                const int t = flat ? 0 : m_tile - img * prm.tiles_per_img;
+                const int off0 = flat ? m_tile * kBM - img * (g.P * g.Q) : t * kBM;
+                const bool two = flat && off0 + kBM > g.P * g.Q && img + 1 < g.N;
                 if constexpr (kStem) {
                     // the input rows this tile adds to the ring (same bookkeeping as the quantizer warps), as boxes of
                     // `stride` rows x all channels; rows outside the image arrive as zeros
@@ -819,12 +826,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     continue;
                 }
                 for (int cb = 0; cb < prm.cblocks; ++cb) {
-                    if (!a_stat) prefetch_next();
+                    if (kPrefetch > 0) prefetch_next();
                     mbar_wait<200>(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
                     mbar_expect_tx(&xfull[xs], x_bytes);
                     // box [128 pixels][KC channels] of image img; pixels beyond H*W are zero-filled
-                    tma_load_3d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], t * kBM, cb * KC, img);
+                    tma_load_3d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], off0, cb * KC, img);
                     if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    if (two) {
+                        mbar_wait<200>(&xempty[xs], xphase ^ 1, prm.err_flag, 6);
+                        mbar_expect_tx(&xfull[xs], x_bytes);
+                        tma_load_3d(xring + (size_t)xs * x_bytes, &tmap_a, &xfull[xs], off0 - g.P * g.Q, cb * KC, img + 1);
+                        if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    }
                 }
             }
         }
@@ -999,10 +1012,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint64_t* const qempty = a_stat ? empty + kAStatBar : empty;
         uint8_t* const qbase = a_stat ? aring : smem;
         const uint32_t q_stride = a_stat ? a_bytes : stage_bytes;
+        const bool flat = prm.tiles_per_img == 0;
+        const int PQf = g.P * g.Q;
         for (int tile = a_stat ? 0 : (int)blockIdx.x; tile < total_tiles; tile += a_stat ? prm.n_tiles : (int)gridDim.x) {
+            // flat pixel tiling: a tile that ends in the next image arrives as two boxes (see the producer); this thread's
+            // 4 pixels (H*W % 4 == 0: never split) come from the first box when they belong to the first image
+            bool two = false, second = false;
+            if (flat) {
+                const int u = prm.fd_ntiles.div(tile);
+                const int m_tile = a_stat ? (int)blockIdx.x + u * (int)gridDim.x : u;
+                const int img = prm.fd_pq.div(m_tile * kBM), off0 = m_tile * kBM - img * PQf;
+                two = off0 + kBM > PQf && img + 1 < g.N;
+                second = two && off0 + lane * 4 >= PQf;
+            }
             for (int cb = 0; cb < prm.cblocks; ++cb) {
                 mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
-                const float* xt = reinterpret_cast<const float*>(xring + (size_t)xs * x_bytes) + (pw * 8) * kBM + lane * 4;
+                const int xs0 = xs;
+                if (two) {
+                    if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
+                    mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
+                }
+                const float* xt = reinterpret_cast<const float*>(xring + (size_t)(second ? xs : xs0) * x_bytes) + (pw * 8) * kBM + lane * 4;
                 float4 v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = lds4(xt + i * kBM);      // explicit LDS.128 (a generic load has several times the latency)
@@ -1012,7 +1042,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 // sleep on any barrier of the CTA, and 512 arrivals per k-block kept the idle epilogue warps spinning
                 // through a third of the issue slots (ncu: 14.6 M NANOSLEEP wake-ups on one layer).
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&xempty[xs]);  // this warp's part of the fp32 tile is in registers
+                if (lane == 0) {
+                    mbar_arrive(&xempty[xs]);  // this warp's part of the fp32 tile is in registers
+                    if (two) mbar_arrive(&xempty[xs0]);
+                }
                 mbar_wait(&qempty[stage], phase ^ 1, prm.err_flag, 5);
                 uint8_t* sa = qbase + (size_t)stage * q_stride;
                 // lanes rotate which of their 4 pixels they store in each step so that one store instruction spreads
@@ -1179,7 +1212,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
             bool row_ok;
             int img, pq;
-            if (kFQ) {  // tiles never straddle images
+            if (kFQ && (kStem || prm.tiles_per_img > 0)) {  // tiles never straddle images
                 img = prm.fd_tpi.div(m_tile);
                 pq = (m_tile - img * prm.tiles_per_img) * kBM + row;
                 row_ok = pq < PQ;
@@ -1592,8 +1625,7 @@ bool umma_stem_supported(const ConvGeom& g, const float* x) {
 // Round 2 (A/B over all 53 layers with the fused variant forced): 1024 -> 256 at 14x14 also wins (72 vs 78 us); layers with
 // several channel tiles (128 -> 512: 113 vs 108 us, 256 -> 1024: 80 vs 72 us) lose because every channel tile quantizes
 // the same pixels again.
-// QB200_ASTAT: 0 = A-stationary mode off (several channel tiles re-quantize, as before), 1 = on (default), 2 = also
-// profitable on 14x14 planes (A/B measurements; the forced fused-quantize algo of the tests takes it on every eligible shape)
+// QB200_ASTAT: 0 = A-stationary mode off (several channel tiles re-quantize, as before), 1 = on (default)
 int a_stat_mode() {
     static const int v = [] {
         const char* e = getenv("QB200_ASTAT");
@@ -1606,10 +1638,10 @@ bool a_stat_fits(const ConvGeom& g) { return g.C / kFqKC <= kMaxStages - kAStatB
 
 bool umma_fused_quant_profitable(const ConvGeom& g) {
     // several channel tiles (K > 256), A-stationary: the pixels are quantized once and the second pass over the input is gone
-    // (128 -> 512 @28x28: 104 vs 108 us).  Not on 14x14 planes: image-aligned 128 + 68-pixel tiles are 512 pixel tiles where
-    // the flat tiling of the two-kernel path has 392, and an output-bound layer pays for every tile's epilogue
-    // (256 -> 1024 @14x14: 79.5 vs 72.5 us).
-    if (g.K > 256 && a_stat_mode() != 0 && a_stat_fits(g) && g.H * g.W >= (a_stat_mode() == 2 ? 196 : 784)) return true;
+    // (with flat pixel tiles: 128 -> 512 @28x28 99 vs 108 us for the two kernels, 256 -> 1024 @14x14 68 vs 72.5 us; with
+    // image-aligned tiles the 14x14 layer took 79.5 us — 512 instead of 392 pixel tiles, and an output-bound layer pays for
+    // every tile's epilogue)
+    if (g.K > 256 && a_stat_mode() != 0 && a_stat_fits(g) && g.H * g.W >= 196) return true;
     if (g.H * g.W >= 784) return g.C == 64 || g.C >= 2 * g.K;
     return g.H * g.W >= 196 && g.C >= 4 * g.K;
 }
@@ -1679,8 +1711,21 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     prm.st_plane_bytes = sp.plane_bytes;
     prm.st_ring = sp.ring;
     { const char* e = getenv("QB200_STEM_DBG"); prm.st_dbg = e ? atoi(e) : 0; }
-    prm.tiles_per_img = fq ? (g.P * g.Q + kBM - 1) / kBM : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
-    prm.m_tiles = (fq || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
+    // fused quantize on planes that are not a multiple of 128 pixels: flat pixel tiling (a tile may end in the next image and
+    // then arrives as two boxes) instead of image-aligned tiles — 14x14: 392 instead of 512 pixel tiles per 256 images,
+    // 28x28: 6.125 instead of 7 per image.  Needs planes of at least one tile (at most two images per tile) and four fp32
+    // slots (checked below).  QB200_FQ_FLAT=0 keeps the image-aligned tiles (A/B measurements).
+    static const bool fq_flat_on = [] {
+        const char* e = getenv("QB200_FQ_FLAT");
+        return !(e && e[0] == '0');
+    }();
+    // (only where image-aligned tiles waste more than 5 % of their rows — 14x14: 31 %, 28x28: 14 %; at 56x56 (2 %) the
+    // second box of every other tile costs more ring depth than the tiles save: 64 -> 256 200 vs 206 us)
+    const int aligned_rows = (g.P * g.Q + kBM - 1) / kBM * kBM;
+    bool fq_flat = fq && !stem && fq_flat_on && g.P * g.Q >= kBM && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q &&
+                   prm.M < (1ll << 31) - kBM;
+    prm.tiles_per_img = fq ? (fq_flat ? 0 : (g.P * g.Q + kBM - 1) / kBM) : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
+    prm.m_tiles = ((fq && !fq_flat) || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
     // out-channel tile: as wide as TMEM allows (fewest re-reads of A) unless that leaves SMs idle
     int BN = g.K >= 256 ? 256 : (g.K > 64 ? 128 : 64);
@@ -1799,7 +1844,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         // one tile's worth plus a slot of lookahead
         const size_t a_b = (size_t)kBM * prm.KC;
         int as = std::min(2 * prm.cblocks, kMaxStages - kAStatBar);
-        while (as > prm.cblocks + 1 && (size_t)as * a_b + 3 * xb + 3 * stage_bytes > ring_budget) --as;
+        while (as > prm.cblocks + 1 && (size_t)as * a_b + (fq_flat ? 4 : 3) * xb + 3 * stage_bytes > ring_budget) --as;
         if (as < prm.cblocks + 1 && prm.cblocks + 1 <= kMaxStages - kAStatBar) as = prm.cblocks + 1;
         as = std::max(as, prm.cblocks);
         QB_REQUIRE((size_t)as * a_b + 2 * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
@@ -1814,6 +1859,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         while (xs > (a_stat ? 2 : 3) && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
+        if (fq_flat && xs < 4) {   // two boxes per k-block need ring depth: back to image-aligned tiles
+            fq_flat = false;
+            prm.tiles_per_img = (g.P * g.Q + kBM - 1) / kBM;
+            prm.m_tiles = g.N * prm.tiles_per_img;
+            prm.fd_tpi = make_fastdiv(prm.tiles_per_img);
+        }
         prm.x_stages = xs;
         ring_budget -= (size_t)xs * xb;
     }
