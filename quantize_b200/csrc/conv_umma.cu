@@ -1773,6 +1773,9 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         if (3 * b1 * g.R * g.S <= room) prm.tap_group = g.R * g.S;
         else if (2 * b1 * g.S <= room) prm.tap_group = g.S;
     }
+    // (measured and not kept: the same decoupled rings for layers with ONE channel tile — deeper weight / A rings behind a
+    // smaller fp32 ring — changed nothing, 47.4 k images/s either way; only 256 -> 128 @56x56 moves, 226 -> 198 us, and it
+    // does so with three fp32 slots instead of five in either mode: fewer reads in flight leave the DRAM queues to its writes)
     const bool a_stat = fq && !stem && prm.n_tiles > 1 && a_stat_mode() != 0 && a_stat_fits(g);
     prm.a_stat = a_stat ? 1 : 0;
     prm.a_slots = 0;
@@ -1855,7 +1858,11 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     if (fq) {
         // fp32 ring: HBM latency x bandwidth needs ~100 KB in flight per SM, so as many 32 KB slots as leave two A/B stages
         // (fused stem: up to kMaxBoxes row boxes in flight — several tiles ahead, the load latency is ~2 tile times)
-        int xs = stem ? kMaxBoxes : kMaxXStages;
+        static const int fq_xmax = [] {      // QB200_FQ_XMAX: cap of the fp32 ring (A/B measurements: ring depth against stages)
+            const char* e = getenv("QB200_FQ_XMAX");
+            return e ? atoi(e) : kMaxXStages;
+        }();
+        int xs = stem ? kMaxBoxes : std::min(kMaxXStages, std::max(fq_xmax, 2));
         while (xs > (a_stat ? 2 : 3) && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
