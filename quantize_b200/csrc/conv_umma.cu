@@ -117,6 +117,9 @@ struct UmmaParams {
     // channel tiles back to back; the quantized A k-blocks live in their own ring of a_slots slots (behind the fp32 ring),
     // are written once per pixel tile and released by the MMAs of the LAST channel tile; stages then hold weights only
     int a_stat, a_slots;
+    // fused quantize, small planes: the quantizer threads fetch their own fp32 values with cp.async (thread-private ring
+    // slots, no TMA boxes, no barriers on the input side); implies flat pixel tiling
+    int x_cpasync;
     int n_acc, acc_stride;  // TMEM accumulator buffers and the columns between them
     int res_async;          // residual tail: stream the identity tensor through a per-warp cp.async ring
     FastDiv fd_ntiles, fd_tpi, fd_pq, fd_q, fd_wp;   // n_tiles, tiles_per_img, P*Q, Q, Wp
@@ -160,6 +163,9 @@ __device__ __forceinline__ void sts2(void* p, uint32_t a, uint32_t b) {
 }
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill(void* dst_smem, const void* src, uint32_t src_bytes) {   // bytes past src_bytes are zeros
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async4(void* dst_smem, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -752,6 +758,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     } else if (lane == 0) {
                         const uint32_t a0 = stage_lo | lo_flag,
                                        b0 = (kStem ? bres16 + (uint32_t)kb * (b_bytes >> 4) : stage_lo + a16) | lo_flag;
+                        if (kFQ && !kStem && (prm.st_dbg & 32)) {   // ablation (bit 5): no MMAs, only the commits
+                        } else
                         if (n_mma == 4) {          // KC = 128
                             umma_i8_lohi(tmem_d, a0, b0, desc_hi, idesc, accumulate);
                             umma_i8_lohi(tmem_d, a0 + 2, b0 + 2, desc_hi, idesc, 1u);
@@ -779,7 +787,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
     } else if (kFQ && warp == 2 + kEpiWarps) {
         // ===================== TMA producer of the fp32 input tiles (fused-quantize variant) =====================
-        if (lane == 0) {
+        if (lane == 0 && (kStem || prm.x_cpasync == 0)) {
             // The shared-memory ring holds only x_stages tiles; HBM latency is covered by prefetching the tiles of the
             // next kPrefetch k-blocks into L2 (the ring loads then hit L2).
             constexpr int kPrefetch = 0;   // measured: prefetching 10 k-blocks ahead thrashes L2 (1.7x DRAM reads); the ring alone is better
@@ -1014,11 +1022,47 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t q_stride = a_stat ? a_bytes : stage_bytes;
         const bool flat = prm.tiles_per_img == 0;
         const int PQf = g.P * g.Q;
-        for (int tile = a_stat ? 0 : (int)blockIdx.x; tile < total_tiles; tile += a_stat ? prm.n_tiles : (int)gridDim.x) {
+        // ---- cp.async input (x_cpasync): every thread streams ITS 8 channels x 4 pixels of each k-block through its own
+        // 128 bytes of the ring slots, x_stages k-blocks ahead — planes of 14x14 / 28x28 pixels as 128-pixel TMA boxes cost
+        // the TMA unit a full 512-byte row per channel whether 8 or 128 of its pixels are valid (two boxes per k-block for a
+        // tile that ends in the next image), and that, not HBM, bounded those layers (1024 -> 256 @14x14: 1.45 us per k-block)
+        const bool xcp = prm.x_cpasync != 0;
+        const int tile_first = a_stat ? 0 : (int)blockIdx.x, tile_step = a_stat ? prm.n_tiles : (int)gridDim.x;
+        struct { int tile, cb, slot; bool live; uint32_t bytes; const float* base; } nx = {0, 0, 0, false, 0u, nullptr};
+        auto nx_set_tile = [&](int t) {
+            nx.tile = t;
+            nx.cb = 0;
+            nx.live = t < total_tiles;
+            if (nx.live) {
+                const int u = prm.fd_ntiles.div(t);
+                const int m_tile = a_stat ? (int)blockIdx.x + u * (int)gridDim.x : u;
+                const int64_t m = (int64_t)m_tile * kBM + lane * 4;               // flat tiling; 4 pixels never straddle images
+                const bool ok = m < prm.M;
+                const int img = ok ? prm.fd_pq.div((int)m) : 0;
+                nx.bytes = ok ? 16u : 0u;                                          // rows past the last pixel: zeros
+                nx.base = prm.x + ((int64_t)img * g.C + pw * 8) * PQf + (ok ? (int)(m - (int64_t)img * PQf) : 0);
+            }
+        };
+        auto nx_issue = [&]() {       // the thread's part of the next k-block (if any); always one commit group
+            if (nx.live) {
+                float* dst = reinterpret_cast<float*>(xring + (size_t)nx.slot * x_bytes) + (pw * 8) * kBM + lane * 4;
+                const float* src = nx.base + (int64_t)nx.cb * kFqKC * PQf;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cp_async16_zfill(dst + i * kBM, src + (int64_t)i * PQf, nx.bytes);
+                if (++nx.cb == prm.cblocks) nx_set_tile(nx.tile + tile_step);
+            }
+            cp_async_commit();
+            if (++nx.slot == prm.x_stages) nx.slot = 0;
+        };
+        if (xcp) {
+            nx_set_tile(tile_first);
+            for (int i = 0; i < prm.x_stages - 1; ++i) nx_issue();
+        }
+        for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
             // flat pixel tiling: a tile that ends in the next image arrives as two boxes (see the producer); this thread's
             // 4 pixels (H*W % 4 == 0: never split) come from the first box when they belong to the first image
             bool two = false, second = false;
-            if (flat) {
+            if (flat && !xcp) {
                 const int u = prm.fd_ntiles.div(tile);
                 const int m_tile = a_stat ? (int)blockIdx.x + u * (int)gridDim.x : u;
                 const int img = prm.fd_pq.div(m_tile * kBM), off0 = m_tile * kBM - img * PQf;
@@ -1026,7 +1070,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 second = two && off0 + lane * 4 >= PQf;
             }
             for (int cb = 0; cb < prm.cblocks; ++cb) {
-                mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
+                if (xcp) {
+                    // refill the slot read in the previous iteration (its values were consumed by the quantizer), then wait
+                    // for this iteration's group: x_stages - 1 younger groups may stay in flight
+                    nx_issue();
+                    switch (prm.x_stages) {
+                        case 2: cp_async_wait<1>(); break;
+                        case 3: cp_async_wait<2>(); break;
+                        case 4: cp_async_wait<3>(); break;
+                        case 5: cp_async_wait<4>(); break;
+                        default: cp_async_wait<5>(); break;
+                    }
+                } else {
+                    mbar_wait(&xfull[xs], xphase, prm.err_flag, 7);
+                }
                 const int xs0 = xs;
                 if (two) {
                     if (++xs == prm.x_stages) { xs = 0; xphase ^= 1; }
@@ -1034,15 +1091,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
                 const float* xt = reinterpret_cast<const float*>(xring + (size_t)(second ? xs : xs0) * x_bytes) + (pw * 8) * kBM + lane * 4;
                 float4 v[8];
+                uint32_t w[4][2];  // [pixel][word]
+                if (prm.st_dbg & 8) {   // ablation (QB200_STEM_DBG bit 3): no shared loads, no quantizer arithmetic
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) w[t][0] = w[t][1] = 0x01010101u * (uint32_t)cb;
+                } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = lds4(xt + i * kBM);      // explicit LDS.128 (a generic load has several times the latency)
-                uint32_t w[4][2];  // [pixel][word]
                 quant_tile<2>(v, w, qp);
+                }
                 // One arrival per WARP (after a warp sync), not per thread: every mbarrier arrival wakes the warps that
                 // sleep on any barrier of the CTA, and 512 arrivals per k-block kept the idle epilogue warps spinning
                 // through a third of the issue slots (ncu: 14.6 M NANOSLEEP wake-ups on one layer).
                 __syncwarp();
-                if (lane == 0) {
+                if (lane == 0 && !xcp) {
                     mbar_arrive(&xempty[xs]);  // this warp's part of the fp32 tile is in registers
                     if (two) mbar_arrive(&xempty[xs0]);
                 }
@@ -1362,6 +1424,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 }
                 if constexpr (kStem) { if (prm.st_dbg & 4) continue; }
+                if constexpr (kFQ && !kStem) { if (prm.st_dbg & 16) continue; }   // ablation (bit 4): no dequantize / stores
                 if (!acc_out && full_c && uniform_ok) {
                     float* o = static_cast<float*>(out) + o_off;
                     // the same two roundings as every other path (dequant_one): t = fma(z_a, wsum, acc); fma(sc, t, bias).
@@ -1724,6 +1787,16 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     const int aligned_rows = (g.P * g.Q + kBM - 1) / kBM * kBM;
     bool fq_flat = fq && !stem && fq_flat_on && g.P * g.Q >= kBM && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q &&
                    prm.M < (1ll << 31) - kBM;
+    // QB200_FQ_CPASYNC: 0 = TMA boxes everywhere, 1 = cp.async input where flat tiles pay (default), 2 = every fused-quantize
+    // layer (A/B measurements; cp.async handles any plane size, a tile may span several small images)
+    static const int fq_cp_mode = [] {
+        const char* e = getenv("QB200_FQ_CPASYNC");
+        return e ? atoi(e) : 1;
+    }();
+    const bool x_cp = fq && !stem && prm.M < (1ll << 31) - kBM &&
+                      (fq_cp_mode == 2 || (fq_cp_mode == 1 && fq_flat_on && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q));
+    prm.x_cpasync = x_cp ? 1 : 0;
+    if (x_cp) fq_flat = true;
     prm.tiles_per_img = fq ? (fq_flat ? 0 : (g.P * g.Q + kBM - 1) / kBM) : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
     prm.m_tiles = ((fq && !fq_flat) || halo) ? g.N * prm.tiles_per_img : (int)ceil_div64(prm.M, kBM);
     const int sms = num_sms();
@@ -1863,10 +1936,14 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             return e ? atoi(e) : kMaxXStages;
         }();
         int xs = stem ? kMaxBoxes : std::min(kMaxXStages, std::max(fq_xmax, 2));
+        // cp.async input: three k-blocks (96 KB) in flight per SM are as good as five (1024 -> 256 @14x14: 66.0 / 68.1 / 69.6 us
+        // with 3 / 4 / 5 slots, 512 -> 256 @28x28: 107.7 / 109.3 / 111.8) — the memory system, not the ring, bounds these
+        // layers — and the freed shared memory becomes operand stages
+        if (x_cp && xs > 3) xs = 3;
         while (xs > (a_stat ? 2 : 3) && (size_t)xs * xb + 2 * stage_bytes > ring_budget) --xs;
         QB_REQUIRE((size_t)xs * xb + 2 * stage_bytes <= ring_budget, QB200_EUNSUPPORTED,
                    "conv_umma: fused-quantize tile does not fit shared memory");
-        if (fq_flat && xs < 4) {   // two boxes per k-block need ring depth: back to image-aligned tiles
+        if (fq_flat && !x_cp && xs < 4) {   // two boxes per k-block need ring depth: back to image-aligned tiles
             fq_flat = false;
             prm.tiles_per_img = (g.P * g.Q + kBM - 1) / kBM;
             prm.m_tiles = g.N * prm.tiles_per_img;
