@@ -4,6 +4,7 @@
 // from shared memory; torch's one-thread-per-output kernel runs at ~1.5 TB/s on B200, this one at the HBM rate.
 // Results are bit-identical to torch.nn.functional.max_pool2d (max is exact; padding behaves as -inf).
 #include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <atomic>
 #include "common.cuh"
@@ -99,6 +100,53 @@ maxpool2d_kernel(const float* __restrict__ x, float* __restrict__ out, int H, in
     }
 }
 
+// 3x3 / stride 2 / pad 1 on even planes (the ResNet stem's pool), streaming form: a lane owns one output column and walks
+// down the plane; per input row it loads the 8 bytes of columns (2q, 2q + 1), takes column 2q - 1 from its left neighbour by
+// shuffle, and keeps the row maximum of the previous odd row as the carry into the next output row.  Every input element
+// is read from HBM exactly once, nothing is staged in shared memory, the loads of four output rows (eight rows of 256
+// contiguous bytes per warp) are in flight before the first max: the band kernel above spent 30 % of its time in its
+// shared-memory passes (245 us on 256 x 64 x 112 x 112 against ~170 us of HBM time).
+constexpr int kStreamRows = 4;   // output rows per batch of loads
+__global__ void __launch_bounds__(256)
+maxpool3x3s2_stream_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t planes, int H, int W, int P, int Q, int groups) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (plane, column group)
+    if (wid >= planes * groups) return;
+    const int64_t plane = wid / groups;
+    const int q = (int)(wid - plane * groups) * 32 + lane;
+    const bool act = q < Q;
+    const float* xp = x + plane * H * W + 2 * q;
+    float* op = out + plane * P * Q + q;
+    const bool edge = lane == 0 && q > 0;                  // the group's first lane has no left neighbour in the warp
+    float carry = -INFINITY;                                // row maximum of input row 2p - 1
+    auto row_max = [&](float2 v, float left) { return max_nan(max_nan(left, v.x), v.y); };
+    for (int p0 = 0; p0 < P; p0 += kStreamRows) {
+        float2 v[2 * kStreamRows];
+        float e[2 * kStreamRows];
+#pragma unroll
+        for (int u = 0; u < 2 * kStreamRows; ++u) {
+            const int h = 2 * p0 + u;
+            v[u] = make_float2(-INFINITY, -INFINITY);
+            e[u] = -INFINITY;
+            if (act && h < H) {
+                asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v[u].x), "=f"(v[u].y) : "l"(xp + (int64_t)h * W));
+                if (edge) e[u] = __ldg(xp + (int64_t)h * W - 1);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamRows; ++u) {
+            float l0 = __shfl_up_sync(0xffffffffu, v[2 * u].y, 1), l1 = __shfl_up_sync(0xffffffffu, v[2 * u + 1].y, 1);
+            if (lane == 0) { l0 = e[2 * u]; l1 = e[2 * u + 1]; }
+            const float m0 = row_max(v[2 * u], l0), m1 = row_max(v[2 * u + 1], l1);
+            const int p = p0 + u;
+            if (act && p < P) op[(int64_t)p * Q] = max_nan(max_nan(carry, m0), m1);
+            carry = m1;
+        }
+    }
+}
+
 // Global average pooling (the op between the last residual stage and the classifier).  Small planes (7x7 = 196 bytes) are
 // a latency problem, not a bandwidth one: a warp that owns one plane has 196 bytes in flight.  So four lanes share a plane
 // (a warp covers 8 consecutive planes = one contiguous span), every lane issues all its loads before the first add, and two
@@ -152,8 +200,25 @@ extern "C" int qb200_maxpool2d_f32(const float* x, int64_t planes, int32_t H, in
     const int P = (H + 2 * pad - kernel) / stride + 1, Q = (W + 2 * pad - kernel) / stride + 1;
     QB_REQUIRE(P >= 1 && Q >= 1, QB200_EINVAL, "maxpool2d: empty output");
     if (planes == 0) return 0;
+    static const bool stream_on = [] {      // QB200_POOL_STREAM=0: the band kernel everywhere (A/B measurements)
+        const char* e = getenv("QB200_POOL_STREAM");
+        return !(e && e[0] == '0');
+    }();
+    if (stream_on && kernel == 3 && stride == 2 && pad == 1 && H % 2 == 0 && W % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0) {
+        const int groups = (Q + 31) / 32;
+        const int64_t warps = planes * groups;
+        QB_REQUIRE((warps + 7) / 8 < (1ll << 31), QB200_EINVAL, "maxpool2d: too many blocks");
+        QB_CUDA(launch_pdl(maxpool3x3s2_stream_kernel, dim3((unsigned)((warps + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, out,
+                           planes, (int)H, (int)W, P, Q, groups));
+        QB_LAUNCH_CHECK();
+        return 0;
+    }
     // as many output rows per block as keep the staged input rows within 32 KB (+ the column-reduced rows: ~5 blocks per SM)
-    const int max_in_rows = std::max(kernel, (32 * 1024) / (W * 4));
+    static const int stage_kb = [] {      // QB200_POOL_STAGE_KB: staged input per block (A/B measurements)
+        const char* e = getenv("QB200_POOL_STAGE_KB");
+        return e ? std::max(atoi(e), 1) : 32;
+    }();
+    const int max_in_rows = std::max(kernel, (stage_kb * 1024) / (W * 4));
     QB_REQUIRE((size_t)kernel * W * 4 <= 200 * 1024, QB200_EUNSUPPORTED, "maxpool2d: rows wider than shared memory allows");
     int band_rows = std::max(1, (max_in_rows - kernel) / stride + 1);
     band_rows = std::min(band_rows, P);

@@ -106,7 +106,8 @@ def test_non_default_stream_and_launch_counter(engine):
 
 
 @pytest.mark.parametrize("shape,k,s,p", [((3, 5, 112, 112), 3, 2, 1), ((2, 3, 17, 23), 3, 2, 1), ((1, 2, 9, 9), 2, 2, 0),
-                                         ((2, 4, 31, 7), 3, 1, 1), ((1, 1, 5, 300), 5, 3, 2), ((2, 2, 224, 224), 3, 2, 1)])
+                                         ((2, 4, 31, 7), 3, 1, 1), ((1, 1, 5, 300), 5, 3, 2), ((2, 2, 224, 224), 3, 2, 1),
+                                         ((2, 3, 6, 66), 3, 2, 1), ((1, 2, 4, 4), 3, 2, 1), ((2, 2, 10, 64), 3, 2, 1)])
 def test_max_pool2d_matches_torch(engine, shape, k, s, p):
     """engine.max_pool2d (the stem's pooling in the packed ResNet forward) == torch.nn.functional.max_pool2d, bit for bit"""
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).cuda()
