@@ -9,6 +9,7 @@
 // reference module (zero padding of the DEQUANTIZED activation, quantconv2d.py:207-210); the dequant uses the same two
 // fused multiply-adds as every other kernel of the engine, so results are bit-identical to the CUDA-core kernel.
 #include <algorithm>
+#include <cstdlib>
 #include "common.cuh"
 #include "conv_common.cuh"
 #include "quant_math.cuh"
@@ -208,6 +209,128 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming form for 3x3 / pad 1 / stride 1 or 2 depthwise layers with one filter per channel (MobileNetV2's): nothing is
+// staged in shared memory.  A lane owns one column and walks down the plane; per input row it loads its fp32 value(s),
+// quantizes them in registers (the engine's exact quantizer), gets the neighbouring columns by shuffle, and adds the three
+// filter rows' dot products to rolling accumulators of the three output rows the input row belongs to — every input
+// element is read once, every output written once, the loads of kDwRows input rows are in flight before the first use.
+// The band kernel above quantized into a shared patch and read every byte back nine times through funnel shifts: 70 %
+// issue-active at 0.8-1.2 TB/s (profiles/r01_ncu_full_prof_dw.csv).
+// Lane groups of G lanes (8 / 16 / 32, the shuffle width) cover one (plane, run of columns): G - 2 outputs per group at
+// stride 1 (the first and last lane only supply neighbours), G - 1 at stride 2 (lane j owns output column c0 - 1 + j and
+// input columns 2 * that and + 1; lane 0 supplies the left neighbour); 32 / G planes per warp for narrow planes.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kDwRows = 8;   // input rows per batch of loads
+
+template <bool kSignedW, int STRIDE, int G>
+__global__ void __launch_bounds__(256)
+conv_dw3_stream_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq, ConvGeom g, EpilogueParams ep,
+                       void* __restrict__ out, int groups_per_plane, int64_t items,
+                       const float* __restrict__ p_scale, const float* __restrict__ p_zero,
+                       const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
+    pdl_launch_dependents();
+    pdl_wait();
+    constexpr int kPPW = 32 / G;                       // planes per warp
+    constexpr int kOut = STRIDE == 1 ? G - 2 : G - 1;  // output columns per group
+    const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
+    const int lane = threadIdx.x & 31, gl = lane & (G - 1), sub = lane / G;
+    const int64_t item = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (set of kPPW planes, column group)
+    if (item >= items) return;
+    const int64_t planes = (int64_t)g.N * g.K;
+    const int64_t pset = item / groups_per_plane;
+    const int cg = (int)(item - pset * groups_per_plane);
+    const int64_t plane = pset * kPPW + sub;
+    const bool plane_ok = plane < planes;
+    const int k = plane_ok ? (int)(plane % g.K) : 0;
+    const int oc = cg * kOut - 1 + gl;                  // this lane's output column (stride 1: also its input column)
+    const bool emit = plane_ok && oc >= 0 && oc < g.Q && (STRIDE == 1 ? (gl >= 1 && gl <= G - 2) : gl >= 1);
+    const int ic = STRIDE * oc;                         // first input column of the lane
+    const bool in0 = plane_ok && ic >= 0 && ic < g.W, in1 = STRIDE == 2 && plane_ok && ic >= 0 && ic + 1 < g.W;
+    const float* xp = x + (plane_ok ? plane : 0) * g.H * g.W + (in0 ? ic : 0);
+    // the filter (value = byte 0 of each tap's padded channel group) and the in-bounds column sums of its rows
+    int w[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const uint8_t b = __ldg(wq + ((int64_t)k * 9 + i) * g.Cgp);
+        w[i] = kSignedW ? (int)(int8_t)b : (int)b;
+    }
+    const bool has_l = STRIDE * oc - 1 >= 0, has_r = STRIDE * oc + 1 < g.W;   // left / right tap column inside the image
+    int cs[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) cs[r] = (has_l ? w[3 * r] : 0) + w[3 * r + 1] + (has_r ? w[3 * r + 2] : 0);
+    const EpilogueScalars es = load_epilogue_scalars(ep);
+    const float scale = __fmul_rn(es.s_a, __ldg(ep.w_scale + (ep.per_tensor_w ? 0 : k)));
+    const float bias = ep.bias ? __ldg(ep.bias + k) : 0.f;
+    const bool acc_out = ep.out_kind == QB200_OUT_ACC;
+    const int64_t obase = (plane_ok ? plane : 0) * g.P * g.Q + (emit ? oc : 0);
+    auto store = [&](int prow, int acc) {     // output row prow of this lane's column
+        if (!emit) return;
+        const int64_t idx = obase + (int64_t)prow * g.Q;
+        if (acc_out) {
+            static_cast<int32_t*>(out)[idx] = acc;
+        } else {
+            float t = (float)acc;
+            if (es.z_a != 0.f) {
+                const int h0 = prow * STRIDE - 1;
+                const int ws = (h0 >= 0 ? cs[0] : 0) + cs[1] + (h0 + 2 < g.H ? cs[2] : 0);
+                t = __fmaf_rn(es.z_a, (float)ws, t);
+            }
+            static_cast<float*>(out)[idx] = epilogue_tail(__fmaf_rn(scale, t, bias), idx, ep);
+        }
+    };
+    auto quant = [&](float v) -> int {
+        if (p.byte_clamp) return quant_int(v, p);       // tight input clamp: already within [qmin, qmax]
+        return (int)(quant_word_exact(v, 0.f, 0.f, 0.f, p.s, p.z, p.lo, p.hi) & 0xFFu);
+    };
+    int acc_a = 0, acc_b = 0;   // stride 1: partial sums of output rows ih - 1 and ih; stride 2: acc_b = row 2p - 1's part of output p
+    for (int h0 = 0; h0 < g.H; h0 += kDwRows) {
+        float v0[kDwRows], v1[STRIDE == 2 ? kDwRows : 1];
+#pragma unroll
+        for (int u = 0; u < kDwRows; ++u) {
+            const bool rok = h0 + u < g.H;
+            v0[u] = 0.f;
+            if (STRIDE == 2) {
+                v1[u] = 0.f;
+                if (rok && in1) {
+                    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v0[u]), "=f"(v1[u]) : "l"(xp + (int64_t)(h0 + u) * g.W));
+                } else if (rok && in0) {
+                    v0[u] = __ldg(xp + (int64_t)(h0 + u) * g.W);
+                }
+            } else if (rok && in0) {
+                asm("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v0[u]) : "l"(xp + (int64_t)(h0 + u) * g.W));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kDwRows; ++u) {
+            const int ih = h0 + u;
+            if (ih >= g.H) break;                       // (uniform)
+            // quantized taps of this input row: pixels outside the image are 0 (they add nothing, and the zero-point term
+            // counts in-bounds taps only)
+            if (STRIDE == 1) {
+                const int a = in0 ? quant(v0[u]) : 0;
+                const int l = __shfl_up_sync(0xffffffffu, a, 1, G), r = __shfl_down_sync(0xffffffffu, a, 1, G);
+                const int t0 = w[0] * l + w[1] * a + w[2] * r, t1 = w[3] * l + w[4] * a + w[5] * r, t2 = w[6] * l + w[7] * a + w[8] * r;
+                if (ih >= 1) store(ih - 1, acc_a + t2);
+                acc_a = acc_b + t1;
+                acc_b = t0;
+            } else {
+                const int a0 = in0 ? quant(v0[u]) : 0, a1 = in1 ? quant(v1[u]) : 0;
+                const int l = __shfl_up_sync(0xffffffffu, a1, 1, G);
+                if ((ih & 1) == 0) {                    // row 2p: filter row 1 of output p
+                    acc_a = acc_b + w[3] * l + w[4] * a0 + w[5] * a1;
+                } else {                                // row 2p + 1: filter row 2 of output p, filter row 0 of output p + 1
+                    store(ih >> 1, acc_a + w[6] * l + w[7] * a0 + w[8] * a1);
+                    acc_b = w[0] * l + w[1] * a0 + w[2] * a1;
+                }
+            }
+        }
+    }
+    if (STRIDE == 1) store(g.H - 1, acc_a);             // the last output row has no row below it
+    else if (g.H & 1) store(g.H >> 1, acc_a);           // odd H: output row (H - 1) / 2 ends on the last input row
+}
+
 }  // namespace
 
 bool dw_fused_supported(const ConvGeom& g) { return g.groups == g.C && g.Cg == 1 && g.groups > 1 && g.K <= 65535 && g.N <= 65535; }
@@ -217,6 +340,35 @@ int launch_conv_dw_fused(const ConvGeom& g, const float* x, const uint8_t* wq, c
     QB_REQUIRE(dw_fused_supported(g), QB200_EUNSUPPORTED, "conv_dw: not a depthwise layer");
     QB_REQUIRE(aq && aq->scale && aq->zero && aq->qmin && aq->qmax, QB200_EINVAL, "conv_dw: activation quantizer parameters missing");
     QB_REQUIRE(ep.q8_out == nullptr, QB200_EUNSUPPORTED, "conv_dw: no quantized hand-off from depthwise layers");
+    // 3x3 / pad 1 / stride 1 or 2 with one filter per channel: the streaming kernel (QB200_DW_STREAM=0: the band kernel)
+    static const bool stream_on = [] {
+        const char* e = getenv("QB200_DW_STREAM");
+        return !(e && e[0] == '0');
+    }();
+    if (stream_on && g.R == 3 && g.S == 3 && g.pad == 1 && (g.stride == 1 || g.stride == 2) && g.K == g.C &&
+        (g.stride == 1 || (g.W % 2 == 0 && reinterpret_cast<uintptr_t>(x) % 8 == 0)) && (int64_t)g.H * g.W < (1ll << 30)) {
+        const int need = g.stride == 1 ? g.Q + 2 : g.Q + 1;          // lanes one group needs to cover a whole row
+        const int G = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+        const int per_group = g.stride == 1 ? G - 2 : G - 1;
+        const int gpp = (g.Q + per_group - 1) / per_group;
+        const int64_t planes = (int64_t)g.N * g.K;
+        const int64_t items = ((planes + 32 / G - 1) / (32 / G)) * gpp;
+        QB_REQUIRE((items + 7) / 8 < (1ll << 31), QB200_EINVAL, "conv_dw: too many blocks");
+        const dim3 sgrid((unsigned)((items + 7) / 8));
+#define QB_DWS_LAUNCH(SIGNED, ST, GG)                                                                                         \
+        QB_CUDA(launch_pdl(conv_dw3_stream_kernel<SIGNED, ST, GG>, sgrid, dim3(256), 0, st, x, wq, g, ep, out, gpp, items,   \
+                           aq->scale, aq->zero, aq->qmin, aq->qmax))
+#define QB_DWS_G(SIGNED, ST)                                                                                                  \
+        do { if (G == 8) QB_DWS_LAUNCH(SIGNED, ST, 8); else if (G == 16) QB_DWS_LAUNCH(SIGNED, ST, 16); else QB_DWS_LAUNCH(SIGNED, ST, 32); } while (0)
+        if (g.w_sign && g.stride == 1) QB_DWS_G(true, 1);
+        else if (g.w_sign) QB_DWS_G(true, 2);
+        else if (g.stride == 1) QB_DWS_G(false, 1);
+        else QB_DWS_G(false, 2);
+#undef QB_DWS_G
+#undef QB_DWS_LAUNCH
+        QB_LAUNCH_CHECK();
+        return 0;
+    }
     // rows per band: up to 16; channels per block: as many as give ~8K outputs (and fit 40 KB of patch)
     const int TH = std::min(16, g.P);
     const int bands = (g.P + TH - 1) / TH;

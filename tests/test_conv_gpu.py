@@ -202,6 +202,14 @@ DEPTHWISE = [
     (2, 8, 11, 11, 8, 5, 1, 2, 8, 8, 4),        # 5x5 (run-time loops), A4
     (2, 96, 112, 112, 96, 3, 2, 1, 96, 4, 8),   # MobileNetV2 block 2 depthwise at its real spatial size
     (2, 960, 7, 7, 960, 3, 1, 1, 960, 4, 8),    # the 7x7 tail
+    # streaming kernel (3x3, pad 1, one filter per channel): lane-group widths 8 / 16 / 32, several column groups, odd sizes
+    (2, 5, 14, 14, 5, 3, 1, 1, 5, 8, 8),        # stride 1, 16-lane groups, two planes per warp, odd plane count
+    (2, 6, 7, 7, 6, 3, 2, 1, 6, 8, 8),          # stride 2 on odd 7x7 planes: W odd -> the band kernel
+    (3, 7, 14, 14, 7, 3, 2, 1, 7, 4, 8),        # stride 2, 8-lane groups (Q = 7), four planes per warp
+    (1, 3, 56, 70, 3, 3, 1, 1, 3, 8, 8),        # stride 1, three column groups of 30 (70 columns)
+    (2, 4, 33, 64, 4, 3, 2, 1, 4, 8, 8),        # stride 2, odd H (last output row ends on the last input row), Q = 32: two groups
+    (1, 2, 112, 112, 2, 3, 1, 1, 2, 8, 4),      # stride 1 at 112x112, A4
+    (2, 9, 28, 28, 9, 3, 2, 1, 9, 8, 8),        # stride 2, Q = 14: 16-lane groups
 ]
 
 
