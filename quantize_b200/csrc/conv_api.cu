@@ -147,7 +147,7 @@ int run_conv(const qb200_conv_shape* s, const uint8_t* q, bool from_ws, const vo
     }
     if (x_fused && dw_single_kernel(g)) return launch_conv_dw_fused(g, x_fused, wq, ep, aq, out, st);
     if (x_fused && stem_single_kernel(g, x_fused)) return launch_conv_umma(g, nullptr, wq + L.wcol_off, ep, out, st, L.Kcol, x_fused, aq);
-    if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq);
+    if (x_fused) return launch_conv_umma(g, nullptr, wq, ep, out, st, 0, x_fused, aq, false, 1, g_conv_algo == QB200_ALGO_UMMA_FUSED_QUANT);
     if (from_ws && workspace_is_im2col(g, L)) return launch_conv_umma(g, q, wq + L.wcol_off, ep, out, st, L.Kcol);
     // strided 1x1 layers read a compact buffer holding only the sampled pixels: a stride-1 conv over [N, P, Q, Cp]
     if (from_ws && workspace_is_padded(g) && L.tapKC) return launch_conv_umma(g, q, wq + L.wtap_off, ep, out, st, 0, nullptr, nullptr, true);

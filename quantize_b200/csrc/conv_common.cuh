@@ -135,9 +135,11 @@ int launch_conv_direct(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, 
 // halo: qa is the zero-padded NHWC buffer written by launch_act_quantize_padded (see umma_halo_supported).
 // pair_mode: CTA-pair variant (tcgen05.mma.cta_group::2) — 0 never, 1 where it was measured to win (deep spatial kernels
 // with 256-wide channel tiles), 2 wherever it is supported (tests).
+// fq_force: the fused-quantize modes that are gated on the problem size (A-stationary channel tiles, flat pixel tiles,
+// cp.async input: only when there is at least one pixel tile per SM) wherever they are supported (tests: small shapes).
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows = 0, const float* x_fused = nullptr,
-                     const qb200_act_quant* aq_fused = nullptr, bool halo = false, int pair_mode = 1);
+                     const qb200_act_quant* aq_fused = nullptr, bool halo = false, int pair_mode = 1, bool fq_force = false);
 bool umma_halo_supported(const ConvGeom& g);
 bool umma_halo_profitable(const ConvGeom& g);
 int launch_act_quantize_padded(const float* x, const ConvGeom& g, const qb200_act_quant* aq, uint8_t* q, cudaStream_t st);

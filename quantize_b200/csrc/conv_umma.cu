@@ -1704,14 +1704,18 @@ bool umma_fused_quant_profitable(const ConvGeom& g) {
     // (with flat pixel tiles: 128 -> 512 @28x28 99 vs 108 us for the two kernels, 256 -> 1024 @14x14 68 vs 72.5 us; with
     // image-aligned tiles the 14x14 layer took 79.5 us — 512 instead of 392 pixel tiles, and an output-bound layer pays for
     // every tile's epilogue)
-    if (g.K > 256 && a_stat_mode() != 0 && a_stat_fits(g) && g.H * g.W >= 196) return true;
+    // (and only with at least one pixel tile per SM: a CTA runs its pixel tiles' channel tiles one after the other, so with
+    // fewer pixel tiles than SMs the two-kernel path's (pixel tile, channel tile) grid keeps more of the chip busy —
+    // 256 -> 1024 @14x14 at 32 images: 28.8 vs 26.7 us)
+    if (g.K > 256 && a_stat_mode() != 0 && a_stat_fits(g) && g.H * g.W >= 196 && (int64_t)g.N * g.P * g.Q >= (int64_t)kBM * num_sms())
+        return true;
     if (g.H * g.W >= 784) return g.C == 64 || g.C >= 2 * g.K;
     return g.H * g.W >= 196 && g.C >= 4 * g.K;
 }
 
 int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, const EpilogueParams& ep, void* out,
                      cudaStream_t st, int gemm_rows, const float* x_fused, const qb200_act_quant* aq_fused, bool halo,
-                     int pair_mode) {
+                     int pair_mode, bool fq_force) {
     QB_REQUIRE(umma_supported(g), QB200_EUNSUPPORTED, "conv_umma: shape not supported by the tensor-core kernel");
     const bool fq = x_fused != nullptr;
     QB_REQUIRE(!halo || (umma_halo_supported(g) && !fq && gemm_rows == 0), QB200_EINVAL,
@@ -1778,6 +1782,10 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // then arrives as two boxes) instead of image-aligned tiles — 14x14: 392 instead of 512 pixel tiles per 256 images,
     // 28x28: 6.125 instead of 7 per image.  Needs planes of at least one tile (at most two images per tile) and four fp32
     // slots (checked below).  QB200_FQ_FLAT=0 keeps the image-aligned tiles (A/B measurements).
+    // the size-gated fused-quantize modes (flat tiles, cp.async input, A-stationary channel tiles) pay when every SM has at
+    // least one pixel tile; below that (strong-scaled batches) the image-aligned TMA form with narrower channel tiles keeps
+    // more SMs busy (1024 -> 256 @14x14 at 32 images: 43.4 vs 35.9 us)
+    const bool fq_big = fq_force || prm.M >= (int64_t)kBM * num_sms();
     static const bool fq_flat_on = [] {
         const char* e = getenv("QB200_FQ_FLAT");
         return !(e && e[0] == '0');
@@ -1785,7 +1793,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // (only where image-aligned tiles waste more than 5 % of their rows — 14x14: 31 %, 28x28: 14 %; at 56x56 (2 %) the
     // second box of every other tile costs more ring depth than the tiles save: 64 -> 256 200 vs 206 us)
     const int aligned_rows = (g.P * g.Q + kBM - 1) / kBM * kBM;
-    bool fq_flat = fq && !stem && fq_flat_on && g.P * g.Q >= kBM && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q &&
+    bool fq_flat = fq && !stem && fq_flat_on && fq_big && g.P * g.Q >= kBM && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q &&
                    prm.M < (1ll << 31) - kBM;
     // QB200_FQ_CPASYNC: 0 = TMA boxes everywhere, 1 = cp.async input where flat tiles pay (default), 2 = every fused-quantize
     // layer (A/B measurements; cp.async handles any plane size, a tile may span several small images)
@@ -1794,7 +1802,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         return e ? atoi(e) : 1;
     }();
     const bool x_cp = fq && !stem && prm.M < (1ll << 31) - kBM &&
-                      (fq_cp_mode == 2 || (fq_cp_mode == 1 && fq_flat_on && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q));
+                      (fq_cp_mode == 2 || (fq_cp_mode == 1 && fq_flat_on && fq_big && 20 * (aligned_rows - g.P * g.Q) > g.P * g.Q));
     prm.x_cpasync = x_cp ? 1 : 0;
     if (x_cp) fq_flat = true;
     prm.tiles_per_img = fq ? (fq_flat ? 0 : (g.P * g.Q + kBM - 1) / kBM) : (halo ? ((g.P - 1) * prm.Wp + g.Q + kBM - 1) / kBM : 0);
@@ -1820,7 +1828,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
             if (cost < best_cost) { best_cost = cost; best = cand; }
         }
         BN = best;
-    } else if (!(fq && !stem && a_stat_mode() != 0 && a_stat_fits(g))) {
+    } else if (!(fq && !stem && a_stat_mode() != 0 && a_stat_fits(g) && fq_big)) {
         // (fused quantize with the A-stationary mode: a CTA runs all channel tiles of its pixel tiles, narrower tiles add
         // no parallelism — and without it every extra channel tile quantizes the same pixels again)
         while (BN > 64 && (int64_t)prm.m_tiles * ((g.K + BN - 1) / BN) < 2 * sms) BN >>= 1;
@@ -1849,7 +1857,7 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
     // (measured and not kept: the same decoupled rings for layers with ONE channel tile — deeper weight / A rings behind a
     // smaller fp32 ring — changed nothing, 47.4 k images/s either way; only 256 -> 128 @56x56 moves, 226 -> 198 us, and it
     // does so with three fp32 slots instead of five in either mode: fewer reads in flight leave the DRAM queues to its writes)
-    const bool a_stat = fq && !stem && prm.n_tiles > 1 && a_stat_mode() != 0 && a_stat_fits(g);
+    const bool a_stat = fq && !stem && prm.n_tiles > 1 && a_stat_mode() != 0 && a_stat_fits(g) && fq_big;
     prm.a_stat = a_stat ? 1 : 0;
     prm.a_slots = 0;
     const size_t stage_bytes = stem ? (size_t)kBM * prm.KC * prm.cblocks
