@@ -222,7 +222,12 @@ conv_dw_fused_kernel(const float* __restrict__ x, const uint8_t* __restrict__ wq
 // stride 1 (the first and last lane only supply neighbours), G - 1 at stride 2 (lane j owns output column c0 - 1 + j and
 // input columns 2 * that and + 1; lane 0 supplies the left neighbour); 32 / G planes per warp for narrow planes.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kDwRows = 8;   // input rows per batch of loads
+#ifndef QB200_DW_ROWS1
+#define QB200_DW_ROWS1 8
+#endif
+#ifndef QB200_DW_ROWS2
+#define QB200_DW_ROWS2 8
+#endif
 
 template <bool kSignedW, int STRIDE, int G>
 __global__ void __launch_bounds__(256)
@@ -232,6 +237,7 @@ conv_dw3_stream_kernel(const float* __restrict__ x, const uint8_t* __restrict__ 
                        const float* __restrict__ p_qmin, const float* __restrict__ p_qmax) {
     pdl_launch_dependents();
     pdl_wait();
+    constexpr int kDwRows = STRIDE == 1 ? QB200_DW_ROWS1 : QB200_DW_ROWS2;   // input rows per batch of loads
     constexpr int kPPW = 32 / G;                       // planes per warp
     constexpr int kOut = STRIDE == 1 ? G - 2 : G - 1;  // output columns per group
     const QuantParams p = load_params(p_scale, p_zero, p_qmin, p_qmax);
