@@ -38,6 +38,9 @@
 namespace qb200 {
 namespace {
 
+#ifndef QB200_FQ_KPRE
+#define QB200_FQ_KPRE 2   // column groups whose constants the fused-quantize kernel's epilogue fetches ahead (see `fast`)
+#endif
 constexpr int kBM = 128;            // pixels per tile = TMEM lanes = UMMA M
 constexpr int kEpiWarps = 8;        // two warps per TMEM lane quadrant, each owns half of the tile's columns
 constexpr int kThreads = 64 + kEpiWarps * 32;
@@ -1434,7 +1437,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     auto fast = [&](auto kTailTag, auto kZeroTag) {
                         constexpr bool kTail = decltype(kTailTag)::value;
                         constexpr bool kZ = decltype(kZeroTag)::value;     // activation zero point != 0
-                        constexpr int kPre = (kFQ || kGroups > 1) ? 2 : (kZ ? 4 : 8);
+                        constexpr int kPre = kFQ ? QB200_FQ_KPRE : (kGroups > 1 ? 2 : (kZ ? 4 : 8));
 #pragma unroll
                         for (int g0 = 0; g0 < 8; g0 += kPre) {
                             float4 S[kPre], B[kPre], Wz[kZ ? kPre : 1];
@@ -1920,7 +1923,12 @@ int launch_conv_umma(const ConvGeom& g, const uint8_t* qa, const uint8_t* wq, co
         else if (res4_on && reinterpret_cast<uintptr_t>(ep.residual) % 4 == 0) prm.res_async = 2;
     }
     const size_t tail = kTailBytes + 2 * (size_t)prm.wcls_smem + (prm.res_async ? kResBytes : 0) + (stem ? (size_t)sp.plane_bytes : 0);
-    size_t ring_budget = ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget) - 1024 - tail - b_res;
+    static const size_t fq_budget = [] {      // QB200_FQ_SMEM_KB: shared-memory budget of the fused-quantize kernel (A/B measurements)
+        const char* e = getenv("QB200_FQ_SMEM_KB");
+        const size_t v = e ? (size_t)atoi(e) * 1024 : kSmemBudgetFq;
+        return v < 96 * 1024 ? (size_t)96 * 1024 : (v > kSmemBudgetFq ? kSmemBudgetFq : v);
+    }();
+    size_t ring_budget = (fq && !stem ? fq_budget : ((fq || prm.res_async) ? kSmemBudgetFq : kSmemBudget)) - 1024 - tail - b_res;
     // ring slot of the fp32 input: a [64 channels][128 pixels] tile, or (fused stem) one box of `stride` rows x all channels
     const size_t xb = stem ? (size_t)((sp.box_bytes + 127) & ~127) : (size_t)kFqKC * kBM * 4;
     if (a_stat) {
