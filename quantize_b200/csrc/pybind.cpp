@@ -494,6 +494,7 @@ at::Tensor quantconv2d_float_input(const at::Tensor& input, const at::Tensor& we
 // result (the residual path needs it) and the consumer's quantized workspace; the call returns (out, workspace|None)
 // and a later chain starting with that layer takes the workspace as input_handoff (its `input` is then only used for
 // the shape).
+
 // ------------------------------------------------------------------------------------------------
 struct ChainLayer {
     at::Tensor weight, des, scale, zero;
@@ -640,6 +641,78 @@ py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, co
     if (!emit) return py::cast(out);
     return py::make_tuple(out, ws_emit.defined() ? py::cast(ws_emit) : py::none());
 }
+
+// quantconv2d_u8_nhwc (engine extension): a fused quantized conv whose input is ALREADY quantized — the NHWC(Cp) byte
+// workspace another layer's epilogue wrote with this very activation quantizer (quantconv2d_chain's emit_next).  Used for
+// the 1x1 / stride-2 shortcut conv of a down-sampling residual block: its quantizer sees the same tensor as the block's
+// conv1 and, calibrated on the same data, has bit-identical parameters, so conv1's hand-off bytes serve both and the
+// separate quantizer pass over the fp32 tensor disappears.  `layer` is a chain_args 12-tuple; in_shape = (N, C, H, W).
+at::Tensor quantconv2d_u8_nhwc(const at::Tensor& q_nhwc, const std::vector<int64_t>& in_shape, const py::tuple& layer) {
+    CHECK_INPUT(q_nhwc);
+    TORCH_CHECK(q_nhwc.dtype() == torch::kByte, "q_nhwc must be a uint8 tensor");
+    TORCH_CHECK(in_shape.size() == 4, "in_shape must be (N, C, H, W)");
+    TORCH_CHECK(layer.size() == 12, "layer is a 12-tuple (chain_args)");
+    ChainLayer l;
+    l.weight = layer[0].cast<at::Tensor>();
+    l.des = layer[1].cast<at::Tensor>();
+    l.scale = layer[2].cast<at::Tensor>();
+    l.zero = layer[3].cast<at::Tensor>();
+    if (!layer[4].is_none()) l.bias = layer[4].cast<at::Tensor>();
+    l.stride = layer[5].cast<int>();
+    l.pad = layer[6].cast<int>();
+    l.qa = QuantArgs{qparam(layer[7], "input_scale"), qparam(layer[8], "input_zero"), qparam(layer[9], "input_qmin"), qparam(layer[10], "input_qmax")};
+    TORCH_CHECK(!l.qa.scale.none && !l.qa.zero.none && !l.qa.qmin.none && !l.qa.qmax.none,
+                "quantconv2d_u8_nhwc: the activation quantizer parameters are needed (scale and zero point of the bytes)");
+    TORCH_CHECK(!layer[11].cast<bool>(), "quantconv2d_u8_nhwc: no fused ReLU");
+    CHECK_INPUT(l.weight);
+    CHECK_INPUT(l.des);
+    CHECK_INPUT(l.scale);
+    CHECK_INPUT(l.zero);
+    TORCH_CHECK(l.weight.dtype() == torch::kByte, "weight must be a packed uint8 tensor");
+    CHECK_FLOAT(l.scale);
+    CHECK_FLOAT(l.zero);
+    if (l.bias.has_value()) {
+        CHECK_INPUT(l.bias.value());
+        TORCH_CHECK(l.bias.value().dtype() == torch::kFloat32, "bias must be a float tensor");
+    }
+    py::gil_scoped_release nogil;
+    c10::cuda::CUDAGuard guard(q_nhwc.device());
+    void* st = cur_stream();
+    auto dp = host_des(l.des);
+    const std::vector<int64_t>& d = *dp;
+    TORCH_CHECK(d.size() >= 6, "weight_des must hold [n_bits, sign, K, C, R, S]");
+    qb200_conv_shape& s = l.s;
+    s.N = (int32_t)in_shape[0]; s.C = (int32_t)in_shape[1]; s.H = (int32_t)in_shape[2]; s.W = (int32_t)in_shape[3];
+    s.w_bits = (int32_t)d[0];
+    s.w_sign = d[1] != 0;
+    s.K = (int32_t)d[2]; s.Cg = (int32_t)d[3]; s.R = (int32_t)d[4]; s.S = (int32_t)d[5];
+    s.stride = l.stride;
+    s.pad = l.pad;
+    TORCH_CHECK(s.C == s.Cg, "quantconv2d_u8_nhwc: groups must be 1");
+    check_rc(qb200_conv_out_hw(&s, &l.P, &l.Q), "quantconv2d_u8_nhwc");
+    TORCH_CHECK(q_nhwc.numel() >= (int64_t)s.N * s.H * s.W * qb200_padded_channels(s.C),
+                "q_nhwc is smaller than N*H*W*Cp bytes");
+    TORCH_CHECK(l.weight.numel() >= qb200_packed_bytes((int64_t)s.K * s.Cg * s.R * s.S, s.w_bits),
+                "weight is shorter than weight_des describes");
+    const int64_t n_ws = l.scale.numel();
+    TORCH_CHECK(n_ws == 1 || n_ws == s.K, "weight_scale must have 1 or ", s.K, " elements");
+    TORCH_CHECK(l.zero.numel() == n_ws, "weight_zero must have as many elements as weight_scale");
+    if (l.bias.has_value()) TORCH_CHECK(l.bias.value().numel() == s.K, "bias must have ", s.K, " elements");
+    l.pw = prepared_weights(s, l.weight, l.des, l.zero, st);
+    TORCH_CHECK(l.pw->zero_is_zero, "quantconv2d_u8_nhwc needs symmetric weights (weight_zero == 0)");
+    std::vector<at::Tensor> keep;
+    l.aq.scale = device_float(l.qa.scale, q_nhwc.device(), keep);
+    l.aq.zero = device_float(l.qa.zero, q_nhwc.device(), keep);
+    l.aq.qmin = device_float(l.qa.qmin, q_nhwc.device(), keep);
+    l.aq.qmax = device_float(l.qa.qmax, q_nhwc.device(), keep);
+    auto out = at::empty({s.N, s.K, l.P, l.Q}, l.scale.options());
+    const float* bias_p = l.bias.has_value() ? l.bias.value().data_ptr<float>() : nullptr;
+    check_rc(qb200_conv2d_q8_nhwc(&s, q_nhwc.data_ptr<uint8_t>(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(), (int32_t)n_ws,
+                                  bias_p, &l.aq, out.data_ptr(), QB200_OUT_F32, st),
+             "quantconv2d_u8_nhwc");
+    return out;
+}
+
 
 // fake_quantize: Quantizer.simulate of a per-tensor quantizer as one kernel
 at::Tensor fake_quantize(const at::Tensor& input, const py::object& scale, const py::object& zero, const py::object& qmin,
@@ -992,6 +1065,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           "Consecutive fused quantized convs with int8 activations handed from one layer's epilogue to the next.",
           py::arg("input"), py::arg("layers"), py::arg("residual") = py::none(), py::arg("input_handoff") = py::none(),
           py::arg("emit_next") = py::none());
+    m.def("quantconv2d_u8_nhwc", &quantconv2d_u8_nhwc,
+          "Fused quantized conv on an already quantized NHWC(Cp) byte workspace (another layer's hand-off).",
+          py::arg("q_nhwc"), py::arg("in_shape"), py::arg("layer"));
     m.def("fake_quantize", &fake_quantize,
           "(clamp(round(x / scale - zero), qmin, qmax) + zero) * scale for a per-tensor quantizer, one kernel.",
           py::arg("input"), py::arg("scale"), py::arg("zero"), py::arg("qmin"), py::arg("qmax"));

@@ -417,6 +417,33 @@ def _chainable(convs):
     return all(c.packed and c.use_engine and c.symmetric_weights() and c.byte_activations() for c in convs)
 
 
+def _shortcut_shares_handoff(block) -> bool:
+    """Can the 1x1 shortcut conv of a down-sampling block read the int8 hand-off written for the block's conv1?  Needs: an
+    engine-side packed shortcut conv (conv + folded BN) without padding; conv1 a 1x1 / stride-1 / pad-0 conv (its hand-off
+    workspace is then the plain NHWC byte tensor of the block's input); bit-identical activation quantizer parameters
+    (true after calibration on the same data: both quantizers observe the block's input).  Checked once per block."""
+    cached = getattr(block, "_ds_shared", None)
+    if cached is not None:
+        return cached
+    ok = False
+    ds = block.downsample
+    c1 = getattr(block, "conv1", None)
+    if (isinstance(ds, nn.Sequential) and len(ds) >= 1 and isinstance(ds[0], QuantConv2d) and isinstance(c1, QuantConv2d)
+            and all(isinstance(m, nn.Identity) for m in list(ds)[1:])):
+        d = ds[0]
+        ok = (d.packed and d.use_engine and not d.fuse_relu and d.groups == 1 and d.kernel_size == (1, 1) and d.padding == (0, 0)
+              and d.symmetric_weights() and d.byte_activations()
+              and c1.groups == 1 and c1.kernel_size == (1, 1) and c1.stride == (1, 1) and c1.padding == (0, 0)
+              and c1.in_channels == d.in_channels and _chainable((c1,)))
+        if ok:
+            a, b = c1.a_quantizer, d.a_quantizer
+            ok = all(bool(torch.equal(torch.as_tensor(getattr(a, n)).float().reshape(-1).cpu(),
+                                      torch.as_tensor(getattr(b, n)).float().reshape(-1).cpu()))
+                     for n in ("scale", "zero", "qmin", "qmax"))
+    block._ds_shared = ok
+    return ok
+
+
 def _block_convs(block):
     return (block.conv1, block.conv2, block.conv3) if hasattr(block, "conv3") else (block.conv1, block.conv2)
 
@@ -427,8 +454,14 @@ def _block_forward(self, x, handoff=None, next_conv=None):
     quantized, so the intermediates never exist as fp32 tensors (same bits as the unchained path).
     handoff / next_conv (used by _stage_forward): the block's input as the int8 workspace the previous block wrote for
     conv1, and the conv that will consume this block's output — the last epilogue then writes fp32 + int8."""
-    identity = x if self.downsample is None else self.downsample(x)
     convs = _block_convs(self)
+    identity = None
+    if handoff is not None and self.downsample is not None and _shortcut_shares_handoff(self):
+        # the shortcut conv's quantizer has the same parameters as conv1's (both were calibrated on this very tensor): the
+        # bytes the previous block wrote for conv1 are its input too — no quantizer pass over the fp32 tensor
+        identity = _engine.load().quantconv2d_u8_nhwc(handoff, list(x.shape), self.downsample[0].chain_args())
+    if identity is None:
+        identity = x if self.downsample is None else self.downsample(x)
     if getattr(self, "chain", False) and _chainable(convs):
         qe = _engine.load()
         layers = [c.chain_args() for c in convs]

@@ -355,3 +355,30 @@ def test_graphed_forward_on_a_fresh_model_equals_eager():
     with torch.no_grad():
         want = net(x)
     assert torch.equal(outs[0], want) and torch.equal(outs[1], want)
+
+
+def test_shortcut_conv_reads_the_hand_off_of_conv1():
+    """Down-sampling bottlenecks: the 1x1 / stride-2 shortcut conv's quantizer has the same parameters as conv1's (both
+    calibrated on the block's input), so it consumes conv1's int8 hand-off (engine.quantconv2d_u8_nhwc) instead of
+    quantizing the fp32 tensor again.  Logits stay bit-identical to the unchained forward; a block whose shortcut quantizer
+    differs keeps the fp32 path (and the same logits as its own unchained forward)."""
+    net = models.build_packed("resnet50", 8, 8, calib_batch=4, device="cuda", seed=1, fuse_blocks=True, chain_blocks=True,
+                              cross_block=True)
+    ref = models.build_packed("resnet50", 8, 8, calib_batch=4, device="cuda", seed=1, fuse_blocks=True, chain_blocks=False)
+    x = models.synthetic_batch("resnet50", 3, device="cuda")
+    with torch.no_grad():
+        got, want = net(x), ref(x)
+    assert torch.equal(got, want)
+    shared = [b for stage in (net.layer2, net.layer3, net.layer4) for b in stage if getattr(b, "_ds_shared", False)]
+    assert len(shared) == 3, "layer2.0 / layer3.0 / layer4.0 should share conv1's hand-off"
+    assert not getattr(net.layer1[0], "_ds_shared", False)          # fed by the max pool: no hand-off to share
+    # different quantizer parameters -> no sharing, still the right answer
+    blk, rblk = net.layer3[0], ref.layer3[0]
+    for b in (blk, rblk):
+        with torch.no_grad():
+            b.downsample[0].a_quantizer.scale.mul_(1.25)
+    blk._ds_shared = None
+    with torch.no_grad():
+        got2, want2 = net(x), ref(x)
+    assert blk._ds_shared is False
+    assert torch.equal(got2, want2) and not torch.equal(got2, got)
