@@ -509,7 +509,7 @@ struct ChainLayer {
 };
 
 py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, const c10::optional<at::Tensor>& residual,
-                             const c10::optional<at::Tensor>& input_handoff, const py::object& emit_next) {
+                             const c10::optional<at::Tensor>& input_handoff, const py::object& emit_next, const bool emit_only) {
     CHECK_INPUT(input);
     CHECK_FLOAT(input);
     TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
@@ -620,7 +620,9 @@ py::object quantconv2d_chain(const at::Tensor& input, const py::list& layers, co
                 tail.next_workspace = ws_next.data_ptr();
             }
             if (!hand || last) out = at::empty({l.s.N, l.s.K, l.P, l.Q}, input.options());
-            void* out_p = (hand && !last) ? nullptr : out.data_ptr();
+            // emit_only: the caller needs the last layer's result ONLY as the consumer's bytes (the next block reads nothing
+            // else): no fp32 store — `out` is then returned uninitialised, for its shape
+            void* out_p = ((hand && !last) || (hand && last && emit_only)) ? nullptr : out.data_ptr();
             if (last && hand) ws_emit = ws_next;
             if (handed) {
                 check_rc(qb200_conv_from_workspace_ex(&l.s, ws_in.data_ptr(), l.pw->buffer.data_ptr(), l.scale.data_ptr<float>(),
@@ -1064,7 +1066,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("quantconv2d_chain", &quantconv2d_chain,
           "Consecutive fused quantized convs with int8 activations handed from one layer's epilogue to the next.",
           py::arg("input"), py::arg("layers"), py::arg("residual") = py::none(), py::arg("input_handoff") = py::none(),
-          py::arg("emit_next") = py::none());
+          py::arg("emit_next") = py::none(), py::arg("emit_only") = false);
     m.def("quantconv2d_u8_nhwc", &quantconv2d_u8_nhwc,
           "Fused quantized conv on an already quantized NHWC(Cp) byte workspace (another layer's hand-off).",
           py::arg("q_nhwc"), py::arg("in_shape"), py::arg("layer"));

@@ -448,7 +448,7 @@ def _block_convs(block):
     return (block.conv1, block.conv2, block.conv3) if hasattr(block, "conv3") else (block.conv1, block.conv2)
 
 
-def _block_forward(self, x, handoff=None, next_conv=None):
+def _block_forward(self, x, handoff=None, next_conv=None, bytes_only=False):
     """torchvision Bottleneck / BasicBlock forward with the ReLUs and the residual add folded into the convs.
     With `self.chain` the convs run as ONE engine chain: each conv hands its (ReLU'd) result to the next one already
     quantized, so the intermediates never exist as fp32 tensors (same bits as the unchained path).
@@ -466,8 +466,10 @@ def _block_forward(self, x, handoff=None, next_conv=None):
         qe = _engine.load()
         layers = [c.chain_args() for c in convs]
         if next_conv is not None and _chainable((next_conv,)):
+            # bytes_only: the next block reads this block's output only as bytes (see _reads_only_bytes) — the fp32 store of
+            # the last epilogue is skipped and the returned fp32 tensor is uninitialised (shape only)
             return qe.quantconv2d_chain(x.contiguous(), layers, residual=identity.contiguous(), input_handoff=handoff,
-                                        emit_next=next_conv.chain_args())
+                                        emit_next=next_conv.chain_args(), emit_only=bool(bytes_only))
         out = qe.quantconv2d_chain(x.contiguous(), layers, residual=identity.contiguous(), input_handoff=handoff)
         return out if next_conv is None else (out, None)
     out = x
@@ -475,6 +477,14 @@ def _block_forward(self, x, handoff=None, next_conv=None):
         out = c(out)
     out = convs[-1](out, residual=identity)
     return out if next_conv is None else (out, None)
+
+
+def _reads_only_bytes(block) -> bool:
+    """Does `block` read its input only through conv1's int8 hand-off?  True for a chained down-sampling block whose
+    shortcut conv shares that hand-off: conv1 and the shortcut are the only readers of the input (an identity shortcut would
+    add the fp32 tensor itself).  The producing block may then skip its fp32 store."""
+    return (block.downsample is not None and getattr(block, "chain", False) and _chainable(_block_convs(block))
+            and _shortcut_shares_handoff(block))
 
 
 def _resnet_forward_chained(self, x):
@@ -487,7 +497,8 @@ def _resnet_forward_chained(self, x):
     for i, blk in enumerate(blocks):
         nxt = blocks[i + 1] if i + 1 < len(blocks) else None
         if nxt is not None and getattr(blk, "chain", False) and getattr(nxt, "chain", False):
-            x, handoff = blk(x, handoff, nxt.conv1)
+            # (the engine skips the fp32 store only when it does write the hand-off: x is valid whenever handoff is None)
+            x, handoff = blk(x, handoff, nxt.conv1, _reads_only_bytes(nxt))
         else:
             x = blk(x, handoff)
             handoff = None
