@@ -1211,9 +1211,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                     }
                 } else {
                     float* dst = res_s + issue_slot * kResChunkFloats + (lane >> 3) * 32 + 4 * (lane & 7);
+                    if (cur.pix_ok && k + 28 < g.K) {
+                        // whole chunk inside the tensor (the common case): pointer increments instead of a predicate and a
+                        // 64-bit multiply per copy (ncu, conv3 @56x56: 9.6 instructions per copy, 9 % of the kernel's issue slots)
+                        const uint32_t d32 = smem_u32(dst);
+                        const char* sp = reinterpret_cast<const char*>(src);
+                        const int64_t step = (int64_t)PQ * 16;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32 + (uint32_t)i * 512u), "l"(sp) : "memory");
+                            sp += step;
+                        }
+                    } else {
 #pragma unroll
                     for (int i = 0; i < 8; ++i)
                         if (cur.pix_ok && k + 4 * i < g.K) cp_async16(dst + i * 128, src + (int64_t)i * 4 * PQ);
+                    }
                 }
                 if (++cur.c == (cols >> 5)) cur_set_tile(cur.tile + (int)gridDim.x);
             }
@@ -1374,8 +1387,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                         // (kept compact on purpose: the first version branched per element inside the unrolled loop and
                         // the epilogue became instruction-fetch bound — ncu: stall_no_inst on 60 % of its samples)
                         float r[32];
-                        if (uniform_ok) {
-                            // fma(z_a, wsum, acc) is exact (= acc) when z_a == 0, so one form serves both cases
+                        if (uniform_ok && es.z_a == 0.f) {
+                            // zero point 0 (inputs that follow a ReLU — every hand-off layer of a ResNet): fma(z_a, wsum, acc)
+                            // is exactly acc, so the FMA and the window-sum load are skipped (ncu, conv3 @56x56: 5 % of the
+                            // issue slots of an epilogue that is bound by them)
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 s4 = lds4(sc + cc + j), b4 = lds4(br + cc + j);
+                                r[j + 0] = tail(__fmaf_rn(s4.x, (float)(int32_t)v[j + 0], b4.x), j + 0);
+                                r[j + 1] = tail(__fmaf_rn(s4.y, (float)(int32_t)v[j + 1], b4.y), j + 1);
+                                r[j + 2] = tail(__fmaf_rn(s4.z, (float)(int32_t)v[j + 2], b4.z), j + 2);
+                                r[j + 3] = tail(__fmaf_rn(s4.w, (float)(int32_t)v[j + 3], b4.w), j + 3);
+                            }
+                        } else if (uniform_ok) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 s4 = lds4(sc + cc + j), w4 = lds4(wrow + cc + j), b4 = lds4(br + cc + j);
