@@ -735,7 +735,7 @@ at::Tensor fake_quantize(const at::Tensor& input, const py::object& scale, const
 }
 
 // max_pool2d (engine helper for the packed ResNet forward; same result as torch.nn.functional.max_pool2d)
-at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int padding) {
+at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int padding, const c10::optional<at::Tensor>& out_opt) {
     CHECK_INPUT(input);
     CHECK_FLOAT(input);
     TORCH_CHECK(input.dim() == 4, "input must be a 4D tensor");
@@ -745,7 +745,16 @@ at::Tensor max_pool2d(const at::Tensor& input, int kernel, int stride, int paddi
     TORCH_CHECK(kernel >= 1 && stride >= 1 && padding >= 0 && 2 * padding <= kernel, "max_pool2d: bad geometry");
     const int P = (H + 2 * padding - kernel) / stride + 1, Q = (W + 2 * padding - kernel) / stride + 1;
     TORCH_CHECK(P >= 1 && Q >= 1, "max_pool2d: empty output");
-    auto out = at::empty({input.size(0), input.size(1), P, Q}, input.options());
+    at::Tensor out;
+    if (out_opt.has_value()) {   // e.g. a batch slice of a larger tensor (the forward in chunks of images)
+        out = out_opt.value();
+        CHECK_INPUT(out);
+        TORCH_CHECK(out.dtype() == torch::kFloat32 && out.dim() == 4 && out.size(0) == input.size(0) && out.size(1) == input.size(1) &&
+                        out.size(2) == P && out.size(3) == Q && out.device() == input.device(),
+                    "max_pool2d: out must be a contiguous float tensor of the output's shape on the input's device");
+    } else {
+        out = at::empty({input.size(0), input.size(1), P, Q}, input.options());
+    }
     check_rc(qb200_maxpool2d_f32(input.data_ptr<float>(), input.size(0) * input.size(1), H, W, kernel, stride, padding,
                                  out.data_ptr<float>(), cur_stream()),
              "max_pool2d");
@@ -1074,7 +1083,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
           "(clamp(round(x / scale - zero), qmin, qmax) + zero) * scale for a per-tensor quantizer, one kernel.",
           py::arg("input"), py::arg("scale"), py::arg("zero"), py::arg("qmin"), py::arg("qmax"));
     m.def("max_pool2d", &max_pool2d, "fp32 NCHW max pooling (square kernel / stride, -inf padding, floor mode).",
-          py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0);
+          py::arg("input"), py::arg("kernel_size"), py::arg("stride"), py::arg("padding") = 0, py::arg("out") = py::none());
     m.def("avg_pool_global", &avg_pool_global, "fp32 NCHW global average pooling -> [N, C, 1, 1].", py::arg("input"));
     m.def("minmax", &minmax, "The range estimators' (xmin, xmax) in one pass, with the optional running / moving-average update.",
           py::arg("input"), py::arg("granularity"), py::arg("flag"), py::arg("symmetric"), py::arg("update_mode") = 0,

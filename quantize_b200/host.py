@@ -396,10 +396,11 @@ class EngineMaxPool2d(nn.Module):
         assert not pool.ceil_mode and one(pool.dilation) == 1 and not pool.return_indices
         self.kernel_size, self.stride, self.padding = one(pool.kernel_size), one(pool.stride or pool.kernel_size), one(pool.padding)
 
-    def forward(self, x):
+    def forward(self, x, out=None):
         if x.is_cuda and x.dtype == torch.float32:
-            return _engine.load().max_pool2d(x.contiguous(), self.kernel_size, self.stride, self.padding)
-        return torch.nn.functional.max_pool2d(x, self.kernel_size, self.stride, self.padding)
+            return _engine.load().max_pool2d(x.contiguous(), self.kernel_size, self.stride, self.padding, out=out)
+        y = torch.nn.functional.max_pool2d(x, self.kernel_size, self.stride, self.padding)
+        return y if out is None else out.copy_(y)
 
 
 class EngineGlobalAvgPool2d(nn.Module):
@@ -491,7 +492,21 @@ def _resnet_forward_chained(self, x):
     """torchvision ResNet._forward_impl with the int8 hand-off running through ALL residual blocks, also across stage
     boundaries (the first conv of a down-sampling block consumes the previous stage's output like any other conv1;
     its 1x1 stride-2 shortcut conv reads the fp32 tensor)."""
-    x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+    return _resnet_body_chained(self, _resnet_stem(self, x))
+
+
+def _resnet_stem(self, x, out=None):
+    """conv1 -> (folded bn) -> relu -> maxpool; `out`: where the pooled tensor goes (a batch slice when the input arrives in
+    chunks of images — GraphedForward(stem_chunks=...))"""
+    y = self.relu(self.bn1(self.conv1(x)))
+    if out is not None and isinstance(self.maxpool, EngineMaxPool2d):
+        return self.maxpool(y, out=out)
+    y = self.maxpool(y)
+    return y if out is None else out.copy_(y)
+
+
+def _resnet_body_chained(self, x):
+    """everything after the stem's pooling (see _resnet_forward_chained)"""
     blocks = [b for stage in (self.layer1, self.layer2, self.layer3, self.layer4) for b in stage]
     handoff = None
     for i, blk in enumerate(blocks):
@@ -543,6 +558,9 @@ def fuse_resnet_blocks(model, chain=False, cross_block=False):
         stages = (model.layer1, model.layer2, model.layer3, model.layer4)
         if all(hasattr(b, "chain") for stage in stages for b in stage):
             model.forward = types.MethodType(_resnet_forward_chained, model)
+            # stem / body as separate callables: GraphedForward(stem_chunks=...) runs the stem per chunk of images
+            model.qb_stem = types.MethodType(_resnet_stem, model)
+            model.qb_body = types.MethodType(_resnet_body_chained, model)
         else:
             for stage in stages:
                 if all(hasattr(b, "chain") for b in stage):
@@ -563,35 +581,75 @@ class GraphedForward:
     `n_buffers` input buffers, one graph each (the input address is baked into a graph): the H2D copy of step k+1 can fill
     buffer (k+1) % n while graph k % n runs.  Usage:  g = GraphedForward(model, example);  g.input(i).copy_(x);  y = g(i)"""
 
-    def __init__(self, model, example: Tensor, n_buffers=2, warmup=2):
+    def __init__(self, model, example: Tensor, n_buffers=2, warmup=2, stem_chunks=1):
+        """stem_chunks > 1 (models with `qb_stem` / `qb_body`, see fuse_resnet_blocks): the stem (conv1 -> relu -> maxpool)
+        is captured once per chunk of images and writes its slice of the pooled tensor, the rest of the network is one more
+        graph — so the H2D copy of a batch can arrive in chunks and the stem of chunk c runs while chunk c + 1 is still on
+        the wire (the first batch no longer waits for its whole input).  Images are independent: the logits are bit-identical
+        to the one-graph forward.  replay_chunk(i, c) / replay_body(i); __call__ replays everything in order."""
         assert example.is_cuda, "CUDA graphs need CUDA tensors"
         self.model = model
         self.inputs = [torch.empty_like(example) for _ in range(n_buffers)]
         self.inputs[0].copy_(example)
+        n = example.shape[0]
+        chunked = stem_chunks > 1 and hasattr(model, "qb_stem") and hasattr(model, "qb_body") and n % stem_chunks == 0
+        self.stem_chunks = stem_chunks if chunked else 1
         side = torch.cuda.Stream(device=example.device)
         side.wait_stream(torch.cuda.current_stream(example.device))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(max(warmup, 1)):                     # fills the engine's caches (prepared weights, ranges)
-                model(self.inputs[0])
+                y = model(self.inputs[0])
+            if chunked:
+                step = n // stem_chunks
+                pooled_shape = model.qb_stem(self.inputs[0][:step]).shape[1:]
+                for _ in range(max(warmup, 1)):
+                    model.qb_stem(self.inputs[0][:step])
         torch.cuda.current_stream(example.device).wait_stream(side)
         torch.cuda.synchronize(example.device)
-        self.graphs, self.outputs = [], []
+        self.graphs, self.outputs, self.chunk_graphs = [], [], []
         pool = None
         for x in self.inputs:
+            if not chunked:
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, pool=pool):
+                    out = model(x)
+                pool = g.pool()                                    # the graphs run one after the other: share the memory pool
+                self.graphs.append(g)
+                self.outputs.append(out)
+                self.chunk_graphs.append([])
+                continue
+            pooled = torch.empty((n,) + tuple(pooled_shape), device=x.device, dtype=x.dtype)
+            cgs = []
+            for c in range(stem_chunks):
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, pool=pool):
+                    model.qb_stem(x[c * step:(c + 1) * step], out=pooled[c * step:(c + 1) * step])
+                pool = g.pool()
+                cgs.append(g)
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g, pool=pool):
-                out = model(x)
-            pool = g.pool()                                    # the graphs run one after the other: share the memory pool
+                out = model.qb_body(pooled)
+            pool = g.pool()
+            self.chunk_graphs.append(cgs)
             self.graphs.append(g)
             self.outputs.append(out)
 
     def input(self, i=0) -> Tensor:
         return self.inputs[i % len(self.inputs)]
 
-    def __call__(self, i=0) -> Tensor:
-        """replays graph i on the current stream; the returned tensor is overwritten by the next replay"""
+    def replay_chunk(self, i, c):
+        """stem of chunk c of input buffer i (stem_chunks > 1)"""
+        self.chunk_graphs[i % len(self.graphs)][c].replay()
+
+    def replay_body(self, i=0) -> Tensor:
         self.graphs[i % len(self.graphs)].replay()
         return self.outputs[i % len(self.outputs)]
+
+    def __call__(self, i=0) -> Tensor:
+        """replays the forward of input buffer i on the current stream; the returned tensor is overwritten by the next replay"""
+        for g in self.chunk_graphs[i % len(self.graphs)]:
+            g.replay()
+        return self.replay_body(i)
 
 
 def reconstruct(model: nn.Module, w_setting=None, a_setting=None) -> nn.Module:

@@ -382,3 +382,23 @@ def test_shortcut_conv_reads_the_hand_off_of_conv1():
         got2, want2 = net(x), ref(x)
     assert blk._ds_shared is False
     assert torch.equal(got2, want2) and not torch.equal(got2, got)
+
+
+def test_graphed_forward_in_stem_chunks_is_bit_identical():
+    """host.GraphedForward(stem_chunks=4): the stem (conv1 + max pool) replayed per quarter of the batch into slices of the
+    pooled tensor, then the body — same logits, bit for bit, as the eager forward (images are independent)."""
+    net = models.build_packed("resnet50", 8, 8, calib_batch=4, device="cuda", seed=2, fuse_blocks=True, chain_blocks=True,
+                              cross_block=True)
+    x = models.synthetic_batch("resnet50", 8, device="cuda")
+    g = host.GraphedForward(net, torch.zeros_like(x), n_buffers=2, stem_chunks=4)
+    assert g.stem_chunks == 4
+    with torch.no_grad():
+        want = net(x)
+    for i in range(2):
+        g.input(i).copy_(x)
+        for c in range(4):
+            g.replay_chunk(i, c)
+        assert torch.equal(g.replay_body(i), want)
+        g.input(i).zero_()
+        g.input(i).copy_(x)
+        assert torch.equal(g(i), want)
