@@ -422,13 +422,21 @@ def _shortcut_shares_handoff(block) -> bool:
     """Can the 1x1 shortcut conv of a down-sampling block read the int8 hand-off written for the block's conv1?  Needs: an
     engine-side packed shortcut conv (conv + folded BN) without padding; conv1 a 1x1 / stride-1 / pad-0 conv (its hand-off
     workspace is then the plain NHWC byte tensor of the block's input); bit-identical activation quantizer parameters
-    (true after calibration on the same data: both quantizers observe the block's input).  Checked once per block."""
-    cached = getattr(block, "_ds_shared", None)
-    if cached is not None:
-        return cached
-    ok = False
+    (true after calibration on the same data: both quantizers observe the block's input).  Checked once per block and again
+    whenever a parameter tensor is replaced or modified in place."""
     ds = block.downsample
     c1 = getattr(block, "conv1", None)
+
+    def stamp(q):   # identity + in-place version of the quantizer's parameter tensors (host-side, no synchronisation)
+        return tuple((t.data_ptr(), t._version) if isinstance(t, Tensor) else t
+                     for t in (getattr(q, n, None) for n in ("scale", "zero", "qmin", "qmax")))
+    key = None
+    if isinstance(ds, nn.Sequential) and len(ds) >= 1 and isinstance(ds[0], QuantConv2d) and isinstance(c1, QuantConv2d):
+        key = (stamp(c1.a_quantizer), stamp(ds[0].a_quantizer))
+    cached = getattr(block, "_ds_shared", None)
+    if cached is not None and getattr(block, "_ds_shared_key", None) == key:
+        return cached
+    ok = False
     if (isinstance(ds, nn.Sequential) and len(ds) >= 1 and isinstance(ds[0], QuantConv2d) and isinstance(c1, QuantConv2d)
             and all(isinstance(m, nn.Identity) for m in list(ds)[1:])):
         d = ds[0]
@@ -442,6 +450,7 @@ def _shortcut_shares_handoff(block) -> bool:
                                       torch.as_tensor(getattr(b, n)).float().reshape(-1).cpu()))
                      for n in ("scale", "zero", "qmin", "qmax"))
     block._ds_shared = ok
+    block._ds_shared_key = key
     return ok
 
 

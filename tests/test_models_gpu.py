@@ -377,8 +377,7 @@ def test_shortcut_conv_reads_the_hand_off_of_conv1():
     for b in (blk, rblk):
         with torch.no_grad():
             b.downsample[0].a_quantizer.scale.mul_(1.25)
-    blk._ds_shared = None
-    with torch.no_grad():
+    with torch.no_grad():                       # (the in-place change bumps the tensor's version: the cached answer is dropped)
         got2, want2 = net(x), ref(x)
     assert blk._ds_shared is False
     assert torch.equal(got2, want2) and not torch.equal(got2, got)
